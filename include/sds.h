@@ -1,0 +1,186 @@
+/*
+ * sds.h -- C ABI of libsds.so: the B200 (sm_100a) implementation of the simpleDS
+ * delay-spectrum hot path.
+ *
+ * The reference (rasg-affiliates/simpleDS) is pure Python/numpy and has no FFI
+ * seam; the seam is its Python API.  Every entry point below names the
+ * reference statements it replaces ("ds.py" = simpleDS/delay_spectrum.py,
+ * "utils.py" = simpleDS/utils.py).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented as "host";
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as
+ *     void*); nothing is allocated except inside sds_plan_create;
+ *   - return value: 0 ok, <0 invalid argument / unsupported, >0 a cudaError_t;
+ *     sds_last_error() returns a thread-local message for the last failure;
+ *   - complex numbers are interleaved (re, im); arrays are C-ordered.
+ */
+#ifndef SDS_H
+#define SDS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDS_VERSION 100
+#define SDS_MAX_WINDOWS 64
+#define SDS_MAX_NFREQ 4096
+
+enum sds_dtype { SDS_C64 = 0, SDS_C128 = 1, SDS_F32 = 2, SDS_F64 = 3 };
+enum sds_status { SDS_OK = 0, SDS_EINVAL = -1, SDS_ENOTSUP = -2, SDS_ENOMEM = -3 };
+
+/* pair-selection mode of the averaged cross power (utils.py:281-331 removes the
+ * diagonal; the tutorial's plain mean keeps it) */
+enum sds_pair_mode { SDS_PAIRS_ALL = 0, SDS_PAIRS_NO_AUTOS = 1 };
+/* how the pair sum is evaluated: factorised |sum x|^2 identities, or the
+ * explicit warp-shuffle pair loop */
+enum sds_pair_method { SDS_METHOD_FACTORISED = 0, SDS_METHOD_EXPLICIT = 1 };
+
+typedef struct sds_plan sds_plan;
+typedef void *sds_stream; /* cudaStream_t */
+
+const char *sds_last_error(void);
+int sds_version(void);
+
+/* Plan for delay transforms of length `nfreq` (any 1 <= nfreq <= SDS_MAX_NFREQ;
+ * power-of-two lengths 64..2048 take the fast path).  `math` = SDS_F32 or
+ * SDS_F64 selects the arithmetic; `taper_host` is taper(nfreq) evaluated by the
+ * caller (host, fp64) -- replaces the window broadcast at utils.py:548-552 and
+ * the taper argument of ds.py:3504-3517.  Uploads twiddles and the taper. */
+int sds_plan_create(sds_plan **plan, int nfreq, int math, const double *taper_host);
+int sds_plan_destroy(sds_plan *plan);
+int sds_plan_nfreq(const sds_plan *plan);
+int sds_plan_math(const sds_plan *plan);
+
+/* Spectral-window gather, ds.py:3315-3338 (_take_spectral_windows_from_data_like_array):
+ * in  (nspw_in,  nrows, nfreq_in), out (nspw_out, nrows, nfreq_out),
+ * out[s, r, f] = in[c / nfreq_in, r, c % nfreq_in], c = chans[s * nfreq_out + f]
+ * (`chans`: device int32, the flattened freq_chans of ds.py:3264-3270).
+ * elem_bytes in {1, 4, 8, 16}. */
+int sds_take_windows(const void *in, void *out, int elem_bytes, int64_t nrows,
+                     int nspw_in, int nfreq_in, const int32_t *chans, int nspw_out,
+                     int nfreq_out, sds_stream stream);
+
+/* Delay transform, utils.py:509-566 + the flag mask of ds.py:3503-3517.
+ * forward: out[w, r, k'] = delta_x * sum_n in[r, win_start[w] + n] * (1 - flag) *
+ *          taper[n] * exp(-2 pi i (k' - N/2) n / N)         (fft, fftshift, * dx)
+ * inverse: ifftshift(ifft(in * (1 - flag))) / taper * delta_x  (utils.py:561-564,
+ *          including its quirks).
+ * in: `in_dtype` SDS_C64|SDS_C128, rows `in_row_stride` elements apart;
+ * flags: uint8 (numpy bool), nullable, rows `flag_row_stride` elements apart;
+ * win_start: HOST int32[nwin], nwin <= SDS_MAX_WINDOWS;
+ * out: [nwin][nrows][N], SDS_C64 for an SDS_F32 plan, SDS_C128 for SDS_F64. */
+int sds_delay_transform(const sds_plan *plan, const void *in, int in_dtype,
+                        int64_t in_row_stride, const uint8_t *flags,
+                        int64_t flag_row_stride, int64_t nrows, int nwin,
+                        const int32_t *win_start, double delta_x, int inverse,
+                        void *out, int out_dtype, sds_stream stream);
+
+/* Radiometer sigma in Jy, ds.py:3544-3583 (+ utils.py:467-483):
+ * sigma[s,u,p,b,t,f] = coef[s,p,f] / sqrt(int_time[b,t] * nsample[s,u,p,b,t,f]),
+ * non-finite -> 0.  `coef` (device fp64 [S][P][F]) = 1e3 * Tsys * beam_area /
+ * (sqrt(delta_f) * jy_to_mk) is the per-channel part evaluated by the host.
+ * nsample dtype SDS_F32|SDS_F64; sigma_out fp64. */
+int sds_noise_sigma(const double *coef, const double *int_time, const void *nsample,
+                    int nsample_dtype, int S, int U, int P, int B, int T, int F,
+                    double *sigma_out, sds_stream stream);
+
+/* Complex Gaussian realisation, utils.py:486-506: out = sigma * (g1 + i g2) / sqrt(2).
+ * g_re/g_im (device fp64[n]) inject pre-drawn normals (parity mode); when both
+ * are NULL the normals come from Philox4x32-10 keyed by `seed`, counter =
+ * (`offset` + flat index) / 2, Box-Muller.  out dtype SDS_C64|SDS_C128. */
+int sds_generate_noise(const double *sigma, int64_t n, const double *g_re,
+                       const double *g_im, uint64_t seed, uint64_t offset, void *out,
+                       int out_dtype, sds_stream stream);
+
+/* Materialised cross power, utils.py:387-389 as called at ds.py:3620-3633:
+ * out[s,p,i,j,t,d] = a2[s,p,i,t,d] * conj(a1[s,p,j,t,d]).  a1/a2 have element
+ * strides (stride_s, stride_p) over their first two axes and are contiguous in
+ * (B,T,D); dtype SDS_C64|SDS_C128 for inputs and output alike. */
+int sds_cross_power_full(const void *a1, const void *a2, int dtype, int S, int P,
+                         int B, int T, int D, int64_t stride_s, int64_t stride_p,
+                         void *out, sds_stream stream);
+
+/* Materialised thermal estimate, ds.py:3637-3707 + utils.py:230-278.
+ * n1 = nsample of the conj ("j") side, n2 = of the "i" side (same pointer when
+ * Nuv == 1), strides as above, contiguous in (B,T,F).
+ * coef   fp64 [S][P][F] = (1e3 * Tsys * beam_area)^2 * taper^2 * nu^4  (host-made)
+ * freq   fp64 [S][F] in Hz (trapezoid abscissa), int_time fp64 [B][T] (j side),
+ * pol_factor fp64 [P] = 1 / (npols_noise * sqrt(2)).
+ * out fp64 [S][P][B][B][T] in K^2 sr^2 Hz^6; invalid samples are masked out of
+ * the trapezoid (their panels contribute 0). */
+int sds_thermal_power_full(const void *n1, const void *n2, int nsample_dtype,
+                           int64_t stride_s, int64_t stride_p, const double *coef,
+                           const double *freq, const double *int_time,
+                           const double *pol_factor, int S, int P, int B, int T, int F,
+                           double *out, sds_stream stream);
+
+/* Averaged cross power (cross multiply + the user-side mean of the tutorial,
+ * utils.py:387-389 + utils.py:281-331), never materialising the B x B tensor.
+ * Baselines [group_offset[g], group_offset[g+1]) form redundant group g
+ * (device int32[ngroup+1]).  For every (g,s,p,t,d):
+ *   out_all [g,s,p,t,d] = sum_{i,j in g}      a2[i] conj(a1[j])
+ *   out_auto[g,s,p,t,d] = sum_{i in g}        a2[i] conj(a1[i])
+ * (complex128, interleaved).  Means follow on the host as out_all / n^2 or
+ * (out_all - out_auto) / (n (n - 1)).  method = sds_pair_method. */
+int sds_cross_power_avg(const void *a1, const void *a2, int dtype, int S, int P, int B,
+                        int T, int D, int64_t stride_s, int64_t stride_p,
+                        const int32_t *group_offset, int ngroup, int method,
+                        double *out_all, double *out_auto, sds_stream stream);
+
+/* ------------------------------------------------------------------------
+ * Fused engine: window select + flag mask + taper + delay transform + noise
+ * realisation + its transform + pair sums + thermal sums in ONE pass over the
+ * 13 B/sample inputs (ds.py:3196-3338, 3487-3517, 3544-3583, 3585-3707 and
+ * utils.py:387-389, 486-506, 509-560 fused; the B x B tensors of ds.py:399-450
+ * are never formed).
+ * ------------------------------------------------------------------------ */
+typedef struct sds_engine_desc {
+  int32_t npol;        /* polarisations in the batch                            */
+  int32_t nbl;         /* baselines in the batch (all groups, group-sorted)     */
+  int32_t ntime;       /* times in the batch                                    */
+  int32_t nchan;       /* channels per input row (row pitch, samples)           */
+  int32_t nspw;        /* spectral windows, each plan->nfreq channels           */
+  int32_t ngroup;      /* redundant groups                                      */
+  int32_t nuv;         /* 1: auto (one data set); 2: cross of two data sets     */
+  int32_t noise_mode;  /* 0 none, 1 Philox in-kernel, 2 injected (noise_in)     */
+  int32_t win_start[SDS_MAX_WINDOWS];
+  int64_t time_offset; /* global index of the batch's first time (RNG counter)  */
+  int64_t ntime_total; /* global number of times             (RNG counter)      */
+  int64_t bl_offset;   /* global index of the batch's first baseline            */
+  int64_t nbl_total;   /* global number of baselines                            */
+  uint64_t seed;
+  double delta_f;      /* Hz, scales the transform (utils.py:560)               */
+} sds_engine_desc;
+
+/* Inputs: vis  c64 [nuv][npol][nbl][ntime][nchan]; flags u8, nsample f32 same
+ * shape; int_time f32 [nbl][ntime]; group_offset int32[ngroup+1];
+ * sigma_coef fp32 [nspw][npol][N] (as in sds_noise_sigma);
+ * thermal_coef fp64 [nspw][npol][N] (as in sds_thermal_power_full, with the
+ * trapezoid weights NOT folded in), freq fp64 [nspw][N];
+ * noise_in c64 same shape as vis (noise_mode 2 only).
+ * Outputs (fp64, accumulated INTO -- zero them first; sums over the batch's
+ * times): pow_all/pow_auto/noise_all/noise_auto complex [ngroup][nspw][npol][N],
+ * thermal_all/thermal_auto real [ngroup][nspw][npol] (already including the
+ * 1/(npol sqrt2) and 1e-6 factors and the per-baseline 1/t_int).
+ * workspace: sds_engine_workspace_bytes() bytes of device scratch. */
+int64_t sds_engine_workspace_bytes(const sds_plan *plan, const sds_engine_desc *desc);
+int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void *vis,
+                   const uint8_t *flags, const float *nsample, const float *int_time,
+                   const int32_t *group_offset, const float *sigma_coef,
+                   const double *thermal_coef, const double *freq,
+                   const double *pol_factor, const void *noise_in, double *pow_all,
+                   double *pow_auto, double *noise_all, double *noise_auto,
+                   double *thermal_all, double *thermal_auto, void *workspace,
+                   sds_stream stream);
+/* number of kernel launches the last sds_engine_run on this thread enqueued */
+int sds_engine_last_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDS_H */

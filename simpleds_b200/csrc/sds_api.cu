@@ -1,0 +1,100 @@
+// Plan management and the error channel of libsds.so.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "sds_common.cuh"
+
+namespace sds {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *where) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+  return (int)e;
+}
+
+}  // namespace sds
+
+extern "C" const char *sds_last_error(void) { return sds::g_err; }
+extern "C" int sds_version(void) { return SDS_VERSION; }
+
+extern "C" int sds_plan_create(sds_plan **plan, int nfreq, int math, const double *taper_host) {
+  SDS_CHECK_ARG(plan != nullptr, "sds_plan_create: plan is NULL");
+  *plan = nullptr;
+  SDS_CHECK_ARG(nfreq >= 1 && nfreq <= SDS_MAX_NFREQ,
+                "sds_plan_create: nfreq=%d outside [1, %d]", nfreq, SDS_MAX_NFREQ);
+  SDS_CHECK_ARG(math == SDS_F32 || math == SDS_F64,
+                "sds_plan_create: math must be SDS_F32 or SDS_F64, got %d", math);
+  SDS_CHECK_ARG(taper_host != nullptr, "sds_plan_create: taper is NULL");
+
+  sds_plan *pl = (sds_plan *)calloc(1, sizeof(sds_plan));
+  if (!pl) {
+    sds::set_error("sds_plan_create: out of host memory");
+    return SDS_ENOMEM;
+  }
+  sds::Plan &p = pl->p;
+  p.nfreq = nfreq;
+  p.math = math;
+  p.is_pow2 = (nfreq & (nfreq - 1)) == 0;
+
+  // factorise: 4s first, then 2, then odd primes (a large prime factor becomes
+  // one O(r^2) stage -- correct for any length).
+  int n = nfreq, nr = 0;
+  while (n % 4 == 0 && nr < 15) { p.radix[nr++] = 4; n /= 4; }
+  while (n % 2 == 0 && nr < 15) { p.radix[nr++] = 2; n /= 2; }
+  for (int f = 3; (int64_t)f * f <= n && nr < 15; f += 2)
+    while (n % f == 0 && nr < 15) { p.radix[nr++] = f; n /= f; }
+  if (n > 1) p.radix[nr++] = n;
+  p.nradix = nr;
+
+  std::vector<double> tw(2 * (size_t)nfreq);
+  std::vector<float> twf(2 * (size_t)nfreq), tapf(nfreq);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < nfreq; ++k) {
+    long double a = -two_pi * (long double)k / (long double)nfreq;
+    tw[2 * k] = (double)cosl(a);
+    tw[2 * k + 1] = (double)sinl(a);
+    twf[2 * k] = (float)tw[2 * k];
+    twf[2 * k + 1] = (float)tw[2 * k + 1];
+    tapf[k] = (float)taper_host[k];
+  }
+  cudaError_t e;
+#define PLAN_TRY(call)                      \
+  if ((e = (call)) != cudaSuccess) {        \
+    sds_plan_destroy(pl);                   \
+    return sds::cuda_fail(e, #call);        \
+  }
+  PLAN_TRY(cudaMalloc(&p.taper_d, sizeof(double) * nfreq));
+  PLAN_TRY(cudaMalloc(&p.taper_f, sizeof(float) * nfreq));
+  PLAN_TRY(cudaMalloc(&p.twiddle_d, sizeof(double2) * nfreq));
+  PLAN_TRY(cudaMalloc(&p.twiddle_f, sizeof(float2) * nfreq));
+  PLAN_TRY(cudaMemcpy(p.taper_d, taper_host, sizeof(double) * nfreq, cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMemcpy(p.taper_f, tapf.data(), sizeof(float) * nfreq, cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMemcpy(p.twiddle_d, tw.data(), sizeof(double2) * nfreq, cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMemcpy(p.twiddle_f, twf.data(), sizeof(float2) * nfreq, cudaMemcpyHostToDevice));
+#undef PLAN_TRY
+  *plan = pl;
+  return SDS_OK;
+}
+
+extern "C" int sds_plan_destroy(sds_plan *plan) {
+  if (!plan) return SDS_OK;
+  cudaFree(plan->p.taper_d);
+  cudaFree(plan->p.taper_f);
+  cudaFree(plan->p.twiddle_d);
+  cudaFree(plan->p.twiddle_f);
+  free(plan);
+  return SDS_OK;
+}
+
+extern "C" int sds_plan_nfreq(const sds_plan *plan) { return plan ? plan->p.nfreq : SDS_EINVAL; }
+extern "C" int sds_plan_math(const sds_plan *plan) { return plan ? plan->p.math : SDS_EINVAL; }
