@@ -76,7 +76,7 @@ def cross_multiply_array(array_1, array_2=None, axis=0):
     """utils.py:334-393: conj(array_1) x array_2 with a new axis after ``axis``."""
     v1, u1, np1 = _split(array_1)
     if array_2 is None:
-        v2, u2 = v1, Unit("")
+        v2, u2 = v1, u1  # array_2 = deepcopy(array_1) keeps its unit (utils.py:364-377)
     else:
         v2, u2, _ = _split(array_2)
     if tuple(v2.shape) != tuple(v1.shape):
