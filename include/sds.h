@@ -119,6 +119,17 @@ int sds_thermal_power_full(const void *n1, const void *n2, int nsample_dtype,
                            const double *pol_factor, int S, int P, int B, int T, int F,
                            double *out, sds_stream stream);
 
+/* Pair sums of the thermal estimate per (group, spw, pol, time), same inputs as
+ * sds_thermal_power_full plus the group table of sds_cross_power_avg:
+ *   out_all [g,s,p,t] = sum_{i,j in g} thermal[s,p,i,j,t]
+ *   out_auto[g,s,p,t] = sum_{i in g}   thermal[s,p,i,i,t]      (fp64) */
+int sds_thermal_power_avg(const void *n1, const void *n2, int nsample_dtype,
+                          int64_t stride_s, int64_t stride_p, const double *coef,
+                          const double *freq, const double *int_time,
+                          const double *pol_factor, const int32_t *group_offset, int ngroup,
+                          int S, int P, int B, int T, int F, double *out_all,
+                          double *out_auto, sds_stream stream);
+
 /* Averaged cross power (cross multiply + the user-side mean of the tutorial,
  * utils.py:387-389 + utils.py:281-331), never materialising the B x B tensor.
  * Baselines [group_offset[g], group_offset[g+1]) form redundant group g

@@ -1,0 +1,101 @@
+"""Oracle for the batched / fused path.  TEST INFRASTRUCTURE ONLY.
+
+For every redundant group the reference's own sequence is run through the
+restated functions of ``simpleds_oracle`` -- select_spectral_windows ->
+(noise) -> delay_transform -> calculate_delay_spectrum, materialising the
+(Nspws, Npols, Nbls, Nbls, Ntimes, Ndelays) tensors -- and the user-side mean of
+the tutorial (cell 41) / ``utils.remove_auto_correlations`` is taken with numpy.
+Also restates, in numpy float32, the noise stream the fused kernel draws
+(sds_engine.cu) so that the in-kernel realisation can be checked value by value.
+"""
+import numpy as np
+from scipy.signal import windows
+
+from . import simpleds_oracle as orc
+from .philox import philox4x32_10
+
+_LO = np.uint64(0xFFFFFFFF)
+
+
+def group_means(vis, flags, nsample, int_time, group_offset, freq_hz, spectral_windows,
+                polarization_array, trcvr_k, beam_area_sr, taper=windows.blackmanharris,
+                noise_freq=None):
+    """vis/flags/nsample (P,B,T,F0); int_time (B,T); noise_freq: frequency-domain noise
+    (S,P,B,T,N) already window-selected, or None (sigma * 0).  Returns dict of
+    arrays indexed [group] -> (S,P,D) means (all pairs / no autos) and thermal (S,P)."""
+    P, B, T, F0 = vis.shape
+    freq_hz = np.asarray(freq_hz, dtype=np.float64).reshape(1, F0)
+    trcvr = np.broadcast_to(np.asarray(trcvr_k, dtype=np.float64), (F0,)).reshape(1, F0)
+    beam = np.broadcast_to(np.asarray(beam_area_sr, dtype=np.float64), (P, F0)).reshape(1, P, F0)
+    out = {k: [] for k in ("power_all", "power_noautos", "noise_power_all", "noise_power_noautos",
+                           "thermal_all", "thermal_noautos", "sigma")}
+    for g in range(len(group_offset) - 1):
+        b0, b1 = int(group_offset[g]), int(group_offset[g + 1])
+        sl = slice(b0, b1)
+        state = dict(
+            data_array=vis[None, None, :, sl].astype(np.complex128),
+            noise_array=np.zeros((1, 1, P, b1 - b0, T, F0), complex),
+            nsample_array=nsample[None, None, :, sl].astype(np.float64),
+            flag_array=flags[None, None, :, sl].astype(bool),
+            freq_array=freq_hz, trcvr=trcvr, beam_area=beam, beam_sq_area=beam,
+        )
+        state = orc.select_spectral_windows(state, spectral_windows)
+        it = int_time[sl].astype(np.float64)
+        sigma = orc.calculate_noise_power(state["freq_array"], state["trcvr"], state["beam_area"],
+                                          it, state["nsample_array"])
+        if noise_freq is not None:
+            state["noise_array"] = noise_freq[:, None, :, sl].astype(np.complex128)
+        res = orc.calculate_delay_spectrum(
+            state["data_array"], state["noise_array"], state["flag_array"], state["nsample_array"],
+            state["freq_array"], state["trcvr"], state["beam_area"], it, polarization_array, taper,
+        )
+        n = b1 - b0
+        for key, arr in (("power", res["power_array"]), ("noise_power", res["noise_power"])):
+            out[key + "_all"].append(orc.average_power(arr, remove_autos=False))
+            out[key + "_noautos"].append(
+                orc.average_power(arr, remove_autos=True) if n > 1 else np.full(arr.shape[:2] + arr.shape[-1:], np.nan)
+            )
+        th = res["thermal_power"]  # (S,P,B,B,T)
+        out["thermal_all"].append(th.reshape(th.shape[0], th.shape[1], -1).mean(-1))
+        if n > 1:
+            off = ~np.eye(n, dtype=bool)
+            out["thermal_noautos"].append(th[:, :, off].reshape(th.shape[0], th.shape[1], -1).mean(-1))
+        else:
+            out["thermal_noautos"].append(np.full(th.shape[:2], np.nan))
+        out["sigma"].append(sigma[:, 0])
+    return out
+
+
+def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
+                      ntime_total=None, bl_offset=0, nbl_total=None):
+    """The frequency-domain noise the fused kernel realises (before mask and taper):
+    sigma * sqrt(-ln u1) * exp(2 pi i u2), in float32 like the kernel.
+
+    sigma_coef32 (S,P,N) float32; nsample (P,B,T,F0) float32; int_time (B,T) float32.
+    Counter = row_id * N/2 + (f mod N/2), row_id = ((s*P + p)*Bt + b)*Tt + t; the word
+    pair (x,y) serves channel f < N/2 and (z,w) channel f + N/2."""
+    P, B, T, _ = nsample.shape
+    S, N = len(win_start), nfreq
+    Tt = T if ntime_total is None else ntime_total
+    Bt = B if nbl_total is None else nbl_total
+    s_i, p_i, b_i, t_i, f_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
+                                          np.arange(N // 2), indexing="ij")
+    row_id = ((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(Bt)
+              + (b_i + bl_offset).astype(np.uint64)) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
+    ctr = row_id * np.uint64(N // 2) + f_i.astype(np.uint64)
+    r = philox4x32_10((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
+                      np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
+                      np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
+    a = np.concatenate([r[0], r[2]], axis=-1)  # channel f < N/2 then f + N/2
+    b = np.concatenate([r[1], r[3]], axis=-1)
+    f32 = np.float32
+    u1 = (a.astype(f32) * f32(2.3283064365386963e-10) + f32(1.1641532182693481e-10)).astype(f32)
+    w = (-np.log(u1.astype(np.float64))).astype(f32)
+    ang = f32(6.2831853071795865) * (b.astype(f32) * f32(2.3283064365386963e-10))
+    chans = np.asarray(win_start)[:, None] + np.arange(N)
+    ns_w = np.stack([nsample[..., chans[s]] for s in range(S)])  # (S,P,B,T,N)
+    tn = int_time[None, None, :, :, None].astype(f32) * ns_w.astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = sigma_coef32[:, :, None, None, :].astype(f32) * np.sqrt(w) / np.sqrt(tn)
+    amp = np.where(tn > 0, amp, f32(0)).astype(f32)
+    return (amp * np.cos(ang.astype(np.float64)) + 1j * amp * np.sin(ang.astype(np.float64))).astype(np.complex64)

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "sds_cross_power_full": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp]),
     "sds_thermal_power_full": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
                                       _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "sds_thermal_power_avg": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32,
+                                     _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sds_cross_power_avg": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                    _vp, _i32, _i32, _vp, _vp, _vp]),
     "sds_engine_workspace_bytes": (_i64, [_vp, C.POINTER(EngineDesc)]),

@@ -4,7 +4,7 @@
 #include <string.h>
 #include <vector>
 
-#include "sds_common.cuh"
+#include "sds_radix.cuh"
 
 namespace sds {
 
@@ -81,6 +81,17 @@ extern "C" int sds_plan_create(sds_plan **plan, int nfreq, int math, const doubl
   PLAN_TRY(cudaMemcpy(p.taper_f, tapf.data(), sizeof(float) * nfreq, cudaMemcpyHostToDevice));
   PLAN_TRY(cudaMemcpy(p.twiddle_d, tw.data(), sizeof(double2) * nfreq, cudaMemcpyHostToDevice));
   PLAN_TRY(cudaMemcpy(p.twiddle_f, twf.data(), sizeof(float2) * nfreq, cudaMemcpyHostToDevice));
+  if (p.is_pow2 && nfreq >= 64) {
+    const int nt = sds::fft_tw_total(nfreq);
+    std::vector<sds::cpx<float>> tf(nt);
+    std::vector<sds::cpx<double>> td(nt);
+    sds::fill_team_twiddles<float>(nfreq, tf.data());
+    sds::fill_team_twiddles<double>(nfreq, td.data());
+    PLAN_TRY(cudaMalloc(&p.team_tw_f, sizeof(sds::cpx<float>) * nt));
+    PLAN_TRY(cudaMalloc(&p.team_tw_d, sizeof(sds::cpx<double>) * nt));
+    PLAN_TRY(cudaMemcpy(p.team_tw_f, tf.data(), sizeof(sds::cpx<float>) * nt, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.team_tw_d, td.data(), sizeof(sds::cpx<double>) * nt, cudaMemcpyHostToDevice));
+  }
 #undef PLAN_TRY
   *plan = pl;
   return SDS_OK;
@@ -92,6 +103,8 @@ extern "C" int sds_plan_destroy(sds_plan *plan) {
   cudaFree(plan->p.taper_f);
   cudaFree(plan->p.twiddle_d);
   cudaFree(plan->p.twiddle_f);
+  cudaFree(plan->p.team_tw_f);
+  cudaFree(plan->p.team_tw_d);
   free(plan);
   return SDS_OK;
 }

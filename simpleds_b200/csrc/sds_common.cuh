@@ -104,6 +104,8 @@ struct Plan {
   float *taper_f;         // [N] fp32
   double2 *twiddle_d;     // [N] exp(-2 pi i k / N)
   float2 *twiddle_f;
+  cpx<float> *team_tw_f;   // sds_radix.cuh tables (power-of-two lengths 64..4096)
+  cpx<double> *team_tw_d;
   int is_pow2;
 };
 

@@ -1,13 +1,656 @@
-// Fused engine (placeholder).
-#include "sds_common.cuh"
+// Fused engine: one pass over the 13 B/sample inputs (complex64 visibility, u8
+// flag, f32 nsample) produces, per redundant group / spectral window /
+// polarisation / delay, the pair sums of the data power, of a matching noise
+// realisation, and the thermal-noise sums -- the reference's
+//   select_spectral_windows -> generate_noise -> delay_transform ->
+//   calculate_delay_spectrum -> mean over baseline pairs and time
+// (ds.py:3196-3338, 3340-3343, 3487-3583, 3585-3707; utils.py:387-389, 486-566)
+// without any (Nbls x Nbls) tensor.
+//
+// Layout of the work
+//   item   = (group g, window s, pol p, chunk of times); items are claimed from
+//            an atomic counter by "workers" (a row team of max(32, N/8) threads).
+//   step   = one row (N/8 >= 32) or 32/(N/8) rows of the item, staged in shared
+//            memory by 1-D bulk TMA copies (cp.async.bulk, mbarrier complete_tx)
+//            through a ring of STAGES slots per worker.
+//   row    = flag mask * taper * delta_f -> length-N transform in registers and
+//            shared memory (sds_radix.cuh) -> S1 += X, S2 += |X|^2; the same for
+//            the noise row generated in registers (Philox4x32-10 + Box-Muller);
+//            thermal partial sums from nsample.
+//   end of a time: P += |S1|^2 (the sum over ALL ordered pairs factorises),
+//   end of an item: fp64 atomics into the outputs (fftshift = index rotation).
+#include "sds_radix.cuh"
+
+namespace sds {
+
+constexpr int ENG_STAGES = 3;
+constexpr int LEG_DATA = 1, LEG_NOISE = 2, LEG_THERMAL = 4;
+
+struct EngineParams {
+  const float2 *vis;
+  const uint8_t *flags;
+  const float *nsample;
+  const float *int_time;
+  const int32_t *goff;
+  const float *sigma_coef;
+  const float2 *noise_in;
+  const double *pol_factor;
+  const void *taper;      // T[N]
+  const void *tw;         // cpx<T>[fft_tw_total(N)]
+  const float *taper_f;   // float versions for the noise leg
+  const float2 *tw_f;
+  // workspace tables (engine_setup_kernel)
+  const int32_t *item_start;  // [ngroup + 1]
+  const double *wl, *wr;      // [nspw][npol][N] trapezoid-weighted thermal coefficients
+  int *counter;
+  double *pow_all, *pow_auto, *noise_all, *noise_auto, *th_all, *th_auto;
+  int64_t time_offset, ntime_total, bl_offset, nbl_total;
+  double delta_f;
+  uint32_t seed_lo, seed_hi;
+  int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
+  int win_start[SDS_MAX_WINDOWS];
+};
+
+// ---- PTX helpers (mbarrier + 1-D bulk TMA) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> __device__ __forceinline__ T rsqrt_t(float x);
+template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return fast_rsqrt(x); }
+template <> __device__ __forceinline__ double rsqrt_t<double>(float x) { return rsqrt((double)x); }
+
+// ---- setup: item table, thermal weights, counter -------------------------------
+// chunk(g) = clamp(target_rows / n_g, 1, ntime); items(g) = ceil(ntime / chunk) nspw npol
+__device__ __host__ __forceinline__ int eng_chunk(int ng, int ntime, int target_rows) {
+  int c = ng > 0 ? target_rows / ng : ntime;
+  return c < 1 ? 1 : (c > ntime ? ntime : c);
+}
+
+__global__ void engine_setup_kernel(const int32_t *__restrict__ goff, int ngroup, int ntime,
+                                    int nspw, int npol, int N, int target_rows,
+                                    const double *__restrict__ thermal_coef,
+                                    const double *__restrict__ freq, int32_t *item_start,
+                                    double *wl, double *wr, int *counter) {
+  // thermal weights: wl[k] = dnu_k/2 * c[k], wr[k] = dnu_k/2 * c[k+1]; a panel whose
+  // channel factor is not finite is excluded (masked_invalid, ds.py:3697)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nspw * npol * N;
+       i += gridDim.x * blockDim.x) {
+    const int k = i % N, s = i / (N * npol);
+    double a = 0.0, b = 0.0;
+    if (thermal_coef && k < N - 1) {
+      const double c0 = thermal_coef[i], c1 = thermal_coef[i + 1];
+      if (isfinite(c0) && isfinite(c1)) {
+        const double hd = 0.5 * (freq[s * N + k + 1] - freq[s * N + k]);
+        a = hd * c0;
+        b = hd * c1;
+      }
+    }
+    wl[i] = a;
+    wr[i] = b;
+  }
+  if (blockIdx.x == 0) {  // exclusive scan of items per group (ngroup <= 65535: one block)
+    __shared__ int carry, part[1024];
+    if (threadIdx.x == 0) {
+      carry = 0;
+      *counter = 0;
+    }
+    __syncthreads();
+    for (int g0 = 0; g0 < ngroup; g0 += blockDim.x) {
+      const int g = g0 + threadIdx.x;
+      int cnt = 0;
+      if (g < ngroup) {
+        const int ng = goff[g + 1] - goff[g];
+        if (ng > 0) {
+          const int c = eng_chunk(ng, ntime, target_rows);
+          cnt = ((ntime + c - 1) / c) * nspw * npol;
+        }
+      }
+      part[threadIdx.x] = cnt;
+      __syncthreads();
+      for (int off = 1; off < blockDim.x; off <<= 1) {
+        int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+      }
+      if (g < ngroup) item_start[g] = carry + part[threadIdx.x] - cnt;
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) item_start[ngroup] = carry;
+  }
+}
+
+// ---- the fused kernel ---------------------------------------------------------
+template <typename T, int N> struct EngCfg {
+  static constexpr int TPR = N / 8;
+  static constexpr int WORKER = TPR < 32 ? 32 : TPR;   // threads per worker
+  static constexpr int ROWS = WORKER / TPR;            // rows per step
+  static constexpr int THREADS = WORKER < 128 ? 128 : WORKER;
+  static constexpr int NWORKER = THREADS / WORKER;
+  static constexpr int ROWB = 13 * N;                  // vis 8N | nsample 4N | flags N
+  static constexpr int SLOT = ROWS * ROWB;
+  static constexpr int BUF = fft_buf_elems(N) * (int)sizeof(cpx<T>);
+  static constexpr int TW_BYTES = fft_tw_total(N) * (int)sizeof(cpx<T>);
+  static constexpr int TWF_BYTES = fft_tw_total(N) * (int)sizeof(cpx<float>);
+  // per worker: barriers (64 B) | ENG_STAGES slots | 2 exchange buffers per row
+  static constexpr int WORKER_BYTES = 64 + ENG_STAGES * SLOT + 2 * ROWS * BUF;
+  static constexpr int SMEM = ((TW_BYTES + TWF_BYTES + 127) / 128) * 128 + NWORKER * WORKER_BYTES;
+};
+
+template <typename T, int N, int LEGS>
+__global__ void __launch_bounds__(EngCfg<T, N>::THREADS)
+engine_kernel(const __grid_constant__ EngineParams P) {
+  using C = EngCfg<T, N>;
+  constexpr int TPR = C::TPR, WORKER = C::WORKER, ROWS = C::ROWS;
+  constexpr bool SAME = sizeof(T) == sizeof(float);
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  // twiddle tables -> shared memory (conflict-free [m][q][tau] layout)
+  cpx<T> *tw_s = reinterpret_cast<cpx<T> *>(smem);
+  cpx<float> *twf_s = SAME ? reinterpret_cast<cpx<float> *>(smem)
+                           : reinterpret_cast<cpx<float> *>(smem + C::TW_BYTES);
+  for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS) {
+    tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[i];
+    if (!SAME) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
+  }
+  const int wid = threadIdx.x / WORKER, wl = threadIdx.x % WORKER;
+  const int sub = wl / TPR, tau = wl % TPR, bar_id = 1 + wid;
+  unsigned char *wbase = smem + ((C::TW_BYTES + (SAME ? 0 : C::TWF_BYTES) + 127) / 128) * 128 +
+                         (size_t)wid * C::WORKER_BYTES;
+  uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
+  unsigned char *stages = wbase + 64;
+  cpx<T> *bufA = reinterpret_cast<cpx<T> *>(stages + ENG_STAGES * C::SLOT + (size_t)sub * 2 * C::BUF);
+  cpx<T> *bufB = reinterpret_cast<cpx<T> *>(reinterpret_cast<unsigned char *>(bufA) + C::BUF);
+  if (wl == 0) {
+    for (int i = 0; i < ENG_STAGES; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // per-thread constants: taper * delta_f at this thread's 8 channels
+  T tapdf[8];
+  float tapdf_f[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    tapdf[r] = reinterpret_cast<const T *>(P.taper)[tau + TPR * r] * (T)P.delta_f;
+    tapdf_f[r] = P.taper_f[tau + TPR * r] * (float)P.delta_f;
+  }
+  const int total_items = P.item_start[P.ngroup];
+  const int row_bytes = ((LEGS & LEG_DATA) ? 8 * N : 0) +
+                        ((LEGS & (LEG_NOISE | LEG_THERMAL)) ? 4 * N : 0) +
+                        ((LEGS & (LEG_DATA | LEG_NOISE)) ? N : 0);
+  uint32_t gstep = 0;  // steps consumed by this worker since kernel start (slot/parity)
+  __shared__ int item_bcast[C::NWORKER];
+
+  for (;;) {
+    int item;
+    if constexpr (WORKER == 32) {
+      item = 0;
+      if (wl == 0) item = atomicAdd(P.counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    } else {
+      team_sync<WORKER>(bar_id);
+      if (wl == 0) item_bcast[wid] = atomicAdd(P.counter, 1);
+      team_sync<WORKER>(bar_id);
+      item = item_bcast[wid];
+    }
+    if (item >= total_items) break;
+    int lo = 0, hi = P.ngroup;  // largest g with item_start[g] <= item
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.item_start + mid) <= item) lo = mid; else hi = mid;
+    }
+    const int g = lo, b0 = __ldg(P.goff + g), ng = __ldg(P.goff + g + 1) - b0;
+    const int chunk = eng_chunk(ng, P.ntime, P.target_rows);
+    const int nchunks = (P.ntime + chunk - 1) / chunk;
+    const int local = item - __ldg(P.item_start + g);
+    const int tc = local % nchunks, sp = local / nchunks, p = sp % P.npol, s = sp / P.npol;
+    const int t0 = tc * chunk, t1 = min(P.ntime, t0 + chunk);
+    const int steps_per_t = (ng + ROWS - 1) / ROWS, nsteps = (t1 - t0) * steps_per_t;
+    const int wstart = P.win_start[s];
+
+    // producer: lane 0 stages step k (rows i0 .. i0+ROWS-1 of time t)
+    auto issue = [&](int k) {
+      if (wl != 0) return;
+      const uint32_t slot = (gstep + (uint32_t)k) % ENG_STAGES;
+      const int t = t0 + k / steps_per_t, i0 = (k % steps_per_t) * ROWS;
+      const int nact = min(ROWS, ng - i0);
+      mbar_expect_tx(&full[slot], (uint32_t)(nact * row_bytes));
+      for (int rr = 0; rr < nact; ++rr) {
+        const int64_t e = (((int64_t)p * P.nbl + b0 + i0 + rr) * P.ntime + t) * P.nchan + wstart;
+        unsigned char *dst = stages + slot * C::SLOT + rr * C::ROWB;
+        if (LEGS & LEG_DATA) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot]);
+        if (LEGS & (LEG_NOISE | LEG_THERMAL)) tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot]);
+        if (LEGS & (LEG_DATA | LEG_NOISE)) tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot]);
+      }
+    };
+
+    float sigc[8];
+    if (LEGS & LEG_NOISE) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
+        sigc[r] = (fabsf(c) <= 3.0e38f) ? c : 0.f;  // non-finite sigma -> 0 (ds.py:3575-3582)
+      }
+    }
+    cpx<T> S1[8];
+    T S2[8], Pw[8];
+    cpx<float> Sn1[8];
+    float Sn2[8], Pn[8];
+    T tA[8], tAp[8], tB[8], tBp[8], tC[8], tCp[8];
+    double th_all_acc = 0.0, th_auto_acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      S1[r] = {(T)0, (T)0}; S2[r] = (T)0; Pw[r] = (T)0;
+      Sn1[r] = {0.f, 0.f}; Sn2[r] = 0.f; Pn[r] = 0.f;
+      tA[r] = tAp[r] = tB[r] = tBp[r] = tC[r] = tCp[r] = (T)0;
+    }
+
+    for (int k = 0; k < ENG_STAGES - 1 && k < nsteps; ++k) issue(k);
+    for (int step = 0; step < nsteps; ++step) {
+      team_sync<WORKER>(bar_id);  // everyone is done with the slot about to be refilled
+      if (step + ENG_STAGES - 1 < nsteps) issue(step + ENG_STAGES - 1);
+      const uint32_t gs = gstep + (uint32_t)step, slot = gs % ENG_STAGES;
+      const int t = t0 + step / steps_per_t, i = (step % steps_per_t) * ROWS + sub;
+      const bool active = i < ng;
+      const int bl = b0 + (active ? i : 0);
+      float tint = 1.f;
+      if (LEGS & (LEG_NOISE | LEG_THERMAL)) tint = __ldg(P.int_time + (int64_t)bl * P.ntime + t);
+      mbar_wait(&full[slot], (gs / ENG_STAGES) & 1u);
+      const unsigned char *row = stages + slot * C::SLOT + sub * C::ROWB;
+      const float2 *vis_s = reinterpret_cast<const float2 *>(row);
+      const float *ns_s = reinterpret_cast<const float *>(row + 8 * N);
+      const unsigned char *fl_s = row + 12 * N;
+
+      if (LEGS & LEG_DATA) {
+        cpx<T> v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int n = tau + TPR * r;
+          const float2 c = active ? vis_s[n] : make_float2(0.f, 0.f);
+          const T m = (active && fl_s[n] == 0) ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
+          v[r] = {(T)c.x * m, (T)c.y * m};
+        }
+        TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          S1[r] = cadd(S1[r], v[r]);
+          S2[r] += v[r].x * v[r].x + v[r].y * v[r].y;
+        }
+      }
+
+      if (LEGS & LEG_NOISE) {
+        cpx<float> v[8];
+        if (P.noise_mode == 1) {
+          // counter = row_id * N/2 + channel mod N/2 ; words (x,y) -> channel f < N/2,
+          // (z,w) -> f + N/2: both belong to this thread (slots q and q + 4)
+          const uint64_t row_id =
+              ((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
+               (uint64_t)(P.bl_offset + bl)) * (uint64_t)P.ntime_total +
+              (uint64_t)(P.time_offset + t);
+          const float inv_t = tint;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t ctr = row_id * (uint64_t)(N / 2) + (uint64_t)(tau + TPR * q);
+            const u32x4 rn = philox4x32_10({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u},
+                                           P.seed_lo, P.seed_hi);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = q + 4 * h, n = tau + TPR * r;
+              const uint32_t a = h ? rn.z : rn.x, b = h ? rn.w : rn.y;
+              const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+              const float w = -0.69314718055994531f * __log2f(u1);      // -ln u1 >= 0
+              const float tn = inv_t * ns_s[n];
+              float amp = sigc[r] * fast_sqrt(w) * fast_rsqrt(tn);      // sigma * sqrt(-ln u1)
+              if (!(tn > 0.f) || !active || fl_s[n] != 0) amp = 0.f;    // invalid sigma / flagged
+              amp *= tapdf_f[r];
+              float sn, cs;
+              __sincosf(6.2831853071795865f * ((float)b * 2.3283064365386963e-10f), &sn, &cs);
+              v[r] = {amp * cs, amp * sn};
+            }
+          }
+        } else {  // injected freq-domain noise (parity mode): plain loads
+          const int64_t e = (((int64_t)p * P.nbl + bl) * P.ntime + t) * P.nchan + wstart;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int n = tau + TPR * r;
+            const float2 c = active ? P.noise_in[e + n] : make_float2(0.f, 0.f);
+            const float m = (active && fl_s[n] == 0) ? tapdf_f[r] : 0.f;
+            v[r] = {c.x * m, c.y * m};
+          }
+        }
+        TeamFft<float, N>::run(v, reinterpret_cast<cpx<float> *>(bufB),
+                               reinterpret_cast<cpx<float> *>(bufA), twf_s, tau, bar_id);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          Sn1[r] = cadd(Sn1[r], v[r]);
+          Sn2[r] += v[r].x * v[r].x + v[r].y * v[r].y;
+        }
+      }
+
+      if (LEGS & LEG_THERMAL) {
+        const T it = (tint > 0.f) ? (T)1 / (T)tint : (T)0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int n = tau + TPR * r;
+          const float n0 = ns_s[n], n1 = (n + 1 < N) ? ns_s[n + 1] : 0.f;
+          const bool e = active && n0 > 0.f && n1 > 0.f;  // both ends of panel n valid
+          const T a0 = e ? rsqrt_t<T>(n0) : (T)0, a1 = e ? rsqrt_t<T>(n1) : (T)0;
+          tA[r] += a0; tAp[r] += a1;
+          tB[r] += a0 * it; tBp[r] += a1 * it;
+          tC[r] += a0 * a0 * it; tCp[r] += a1 * a1 * it;
+        }
+      }
+
+      if ((step + 1) % steps_per_t == 0) {  // all rows of time t done
+        if (LEGS & LEG_DATA) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            cpx<T> sfull = S1[r];
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              sfull.x += __shfl_xor_sync(0xffffffffu, sfull.x, off);
+              sfull.y += __shfl_xor_sync(0xffffffffu, sfull.y, off);
+            }
+            Pw[r] += sfull.x * sfull.x + sfull.y * sfull.y;
+            S1[r] = {(T)0, (T)0};
+          }
+        }
+        if (LEGS & LEG_NOISE) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            cpx<float> sfull = Sn1[r];
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              sfull.x += __shfl_xor_sync(0xffffffffu, sfull.x, off);
+              sfull.y += __shfl_xor_sync(0xffffffffu, sfull.y, off);
+            }
+            Pn[r] += sfull.x * sfull.x + sfull.y * sfull.y;
+            Sn1[r] = {0.f, 0.f};
+          }
+        }
+        if (LEGS & LEG_THERMAL) {
+          const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N;
+          const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            T a = tA[r], ap = tAp[r], b = tB[r], bp = tBp[r];
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, off);
+              ap += __shfl_xor_sync(0xffffffffu, ap, off);
+              b += __shfl_xor_sync(0xffffffffu, b, off);
+              bp += __shfl_xor_sync(0xffffffffu, bp, off);
+            }
+            const double l = __ldg(wlp + tau + TPR * r), rr = __ldg(wrp + tau + TPR * r);
+            if (sub == 0) th_all_acc += l * (double)a * (double)b + rr * (double)ap * (double)bp;
+            th_auto_acc += l * (double)tC[r] + rr * (double)tCp[r];
+            tA[r] = tAp[r] = tB[r] = tBp[r] = tC[r] = tCp[r] = (T)0;
+          }
+        }
+      }
+    }
+    gstep += (uint32_t)nsteps;
+
+    // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
+    const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int kshift = (tau + TPR * r + N / 2) % N;
+      if (LEGS & LEG_DATA) {
+        T s2 = S2[r];
+#pragma unroll
+        for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (sub == 0) {
+          atomicAdd(P.pow_all + 2 * (obase + kshift), (double)Pw[r]);
+          atomicAdd(P.pow_auto + 2 * (obase + kshift), (double)s2);
+        }
+      }
+      if (LEGS & LEG_NOISE) {
+        float s2 = Sn2[r];
+#pragma unroll
+        for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        if (sub == 0) {
+          atomicAdd(P.noise_all + 2 * (obase + kshift), (double)Pn[r]);
+          atomicAdd(P.noise_auto + 2 * (obase + kshift), (double)s2);
+        }
+      }
+    }
+    if (LEGS & LEG_THERMAL) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        th_all_acc += __shfl_xor_sync(0xffffffffu, th_all_acc, off);
+        th_auto_acc += __shfl_xor_sync(0xffffffffu, th_auto_acc, off);
+      }
+      if ((wl & 31) == 0) {
+        const double f = 1e-6 * __ldg(P.pol_factor + p);
+        const int64_t o = ((int64_t)g * P.nspw + s) * P.npol + p;
+        atomicAdd(P.th_all + o, f * th_all_acc);
+        atomicAdd(P.th_auto + o, f * th_auto_acc);
+      }
+    }
+  }
+}
+
+// workspace layout: [counter 256 B][item_start (ngroup+1) int32, padded][wl][wr]
+struct EngWorkspace {
+  int *counter;
+  int32_t *item_start;
+  double *wl, *wr;
+  int64_t bytes;
+};
+static EngWorkspace carve(void *ws, int ngroup, int nspw, int npol, int N) {
+  EngWorkspace w;
+  unsigned char *b = (unsigned char *)ws;
+  int64_t off = 0;
+  w.counter = (int *)(b + off); off += 256;
+  w.item_start = (int32_t *)(b + off); off += (((int64_t)(ngroup + 1) * 4 + 255) / 256) * 256;
+  w.wl = (double *)(b + off); off += (((int64_t)nspw * npol * N * 8 + 255) / 256) * 256;
+  w.wr = (double *)(b + off); off += (((int64_t)nspw * npol * N * 8 + 255) / 256) * 256;
+  w.bytes = off;
+  return w;
+}
+
 static thread_local int g_last_launches = 0;
-extern "C" int64_t sds_engine_workspace_bytes(const sds_plan *, const sds_engine_desc *) { return 0; }
-extern "C" int sds_engine_run(const sds_plan *, const sds_engine_desc *, const void *,
-                              const uint8_t *, const float *, const float *, const int32_t *,
-                              const float *, const double *, const double *, const double *,
-                              const void *, double *, double *, double *, double *, double *,
-                              double *, void *, sds_stream) {
-  sds::set_error("sds_engine_run: not built yet");
+
+template <typename T, int N, int LEGS>
+static int launch_engine(const EngineParams &P, cudaStream_t st) {
+  using C = EngCfg<T, N>;
+  static bool configured = false;
+  if (!configured) {
+    SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  int dev = 0, nsm = 148, per_sm = 1;
+  SDS_CUDA(cudaGetDevice(&dev));
+  SDS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  SDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, engine_kernel<T, N, LEGS>,
+                                                         C::THREADS, C::SMEM));
+  if (per_sm < 1) {
+    set_error("sds_engine_run: kernel does not fit an SM (smem %d B)", C::SMEM);
+    return SDS_ENOTSUP;
+  }
+  engine_kernel<T, N, LEGS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
+  SDS_LAUNCH_CHECK("engine_kernel");
+  ++g_last_launches;
+  return SDS_OK;
+}
+
+// one launch for the leg mask `legs`; fp32 instantiates the fused masks, fp64
+// (register budget) one leg per launch
+template <typename T, int N>
+static int run_engine_n(EngineParams &P, int legs, cudaStream_t st) {
+  if constexpr (sizeof(T) == sizeof(float)) {
+    switch (legs) {
+      case 1: return launch_engine<T, N, 1>(P, st);
+      case 3: return launch_engine<T, N, 3>(P, st);
+      case 5: return launch_engine<T, N, 5>(P, st);
+      case 7: return launch_engine<T, N, 7>(P, st);
+      default: break;
+    }
+  } else {
+    switch (legs) {
+      case 1: return launch_engine<T, N, 1>(P, st);
+      case 2: return launch_engine<T, N, 2>(P, st);
+      case 4: return launch_engine<T, N, 4>(P, st);
+      default: break;
+    }
+  }
+  set_error("sds_engine_run: leg mask %d is not instantiated", legs);
   return SDS_ENOTSUP;
 }
-extern "C" int sds_engine_last_launches(void) { return g_last_launches; }
+
+template <typename T>
+static int run_engine(int N, EngineParams &P, int legs, cudaStream_t st) {
+  switch (N) {
+    case 64: return run_engine_n<T, 64>(P, legs, st);
+    case 128: return run_engine_n<T, 128>(P, legs, st);
+    case 256: return run_engine_n<T, 256>(P, legs, st);
+    case 512: return run_engine_n<T, 512>(P, legs, st);
+    case 1024: return run_engine_n<T, 1024>(P, legs, st);
+    case 2048: return run_engine_n<T, 2048>(P, legs, st);
+    default:
+      set_error("sds_engine_run: fused path needs nfreq in {64..2048, power of two}, got %d", N);
+      return SDS_ENOTSUP;
+  }
+}
+
+}  // namespace sds
+
+extern "C" int64_t sds_engine_workspace_bytes(const sds_plan *plan, const sds_engine_desc *d) {
+  if (!plan || !d) return SDS_EINVAL;
+  return sds::carve(nullptr, d->ngroup, d->nspw, d->npol, plan->p.nfreq).bytes;
+}
+
+extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, const void *vis,
+                              const uint8_t *flags, const float *nsample, const float *int_time,
+                              const int32_t *group_offset, const float *sigma_coef,
+                              const double *thermal_coef, const double *freq,
+                              const double *pol_factor, const void *noise_in, double *pow_all,
+                              double *pow_auto, double *noise_all, double *noise_auto,
+                              double *thermal_all, double *thermal_auto, void *workspace,
+                              sds_stream stream) {
+  using namespace sds;
+  g_last_launches = 0;
+  SDS_CHECK_ARG(plan && d, "sds_engine_run: NULL plan/desc");
+  const Plan &pl = plan->p;
+  const int N = pl.nfreq;
+  SDS_CHECK_ARG(vis && flags && nsample && group_offset && workspace && pow_all && pow_auto,
+                "sds_engine_run: NULL vis/flags/nsample/group_offset/workspace/pow outputs");
+  SDS_CHECK_ARG(d->npol >= 1 && d->nbl >= 1 && d->ntime >= 1 && d->ngroup >= 1 && d->nspw >= 1 &&
+                    d->nspw <= SDS_MAX_WINDOWS && d->ngroup <= 65535,
+                "sds_engine_run: bad dimensions");
+  SDS_CHECK_ARG(d->noise_mode >= 0 && d->noise_mode <= 2, "sds_engine_run: noise_mode not in 0..2");
+  SDS_CHECK_ARG(d->noise_mode == 0 || (int_time && sigma_coef && noise_all && noise_auto),
+                "sds_engine_run: noise needs int_time, sigma_coef and the noise outputs");
+  SDS_CHECK_ARG(d->noise_mode != 2 || noise_in, "sds_engine_run: noise_mode 2 needs noise_in");
+  const bool thermal = thermal_coef != nullptr;
+  SDS_CHECK_ARG(!thermal || (freq && pol_factor && int_time && thermal_all && thermal_auto),
+                "sds_engine_run: thermal needs freq, pol_factor, int_time and the thermal outputs");
+  if (d->nuv != 1) {
+    set_error("sds_engine_run: the fused path handles nuv == 1 only (got %d)", d->nuv);
+    return SDS_ENOTSUP;
+  }
+  if (!pl.is_pow2 || N < 64 || N > 2048 || !pl.team_tw_f) {
+    set_error("sds_engine_run: fused path needs a power-of-two nfreq in 64..2048, got %d", N);
+    return SDS_ENOTSUP;
+  }
+  // 1-D bulk copies need 16-byte aligned sources for every array (flags are 1 B/sample)
+  if (d->nchan % 16 != 0 || ((uintptr_t)vis | (uintptr_t)flags | (uintptr_t)nsample) % 16 != 0) {
+    set_error("sds_engine_run: fused path needs nchan %% 16 == 0 and 16-byte aligned inputs");
+    return SDS_ENOTSUP;
+  }
+  for (int w = 0; w < d->nspw; ++w) {
+    SDS_CHECK_ARG(d->win_start[w] >= 0 && d->win_start[w] + N <= d->nchan,
+                  "sds_engine_run: window %d [%d, %d) outside the %d channels", w, d->win_start[w],
+                  d->win_start[w] + N, d->nchan);
+    if (d->win_start[w] % 16 != 0) {
+      set_error("sds_engine_run: fused path needs window starts that are multiples of 16");
+      return SDS_ENOTSUP;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  EngWorkspace ws = carve(workspace, d->ngroup, d->nspw, d->npol, N);
+  EngineParams P;
+  P.vis = (const float2 *)vis; P.flags = flags; P.nsample = nsample; P.int_time = int_time;
+  P.goff = group_offset; P.sigma_coef = sigma_coef; P.noise_in = (const float2 *)noise_in;
+  P.pol_factor = pol_factor;
+  P.taper_f = pl.taper_f; P.tw_f = (const float2 *)pl.team_tw_f;
+  if (pl.math == SDS_F64) { P.taper = pl.taper_d; P.tw = pl.team_tw_d; }
+  else { P.taper = pl.taper_f; P.tw = pl.team_tw_f; }
+  P.item_start = ws.item_start; P.wl = ws.wl; P.wr = ws.wr; P.counter = ws.counter;
+  P.pow_all = pow_all; P.pow_auto = pow_auto; P.noise_all = noise_all; P.noise_auto = noise_auto;
+  P.th_all = thermal_all; P.th_auto = thermal_auto;
+  P.time_offset = d->time_offset; P.ntime_total = d->ntime_total > 0 ? d->ntime_total : d->ntime;
+  P.bl_offset = d->bl_offset; P.nbl_total = d->nbl_total > 0 ? d->nbl_total : d->nbl;
+  P.delta_f = d->delta_f; P.seed_lo = (uint32_t)d->seed; P.seed_hi = (uint32_t)(d->seed >> 32);
+  P.npol = d->npol; P.nbl = d->nbl; P.ntime = d->ntime; P.nchan = d->nchan; P.nspw = d->nspw;
+  P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
+  P.target_rows = 64;
+  for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
+
+  const int legs = LEG_DATA | (d->noise_mode ? LEG_NOISE : 0) | (thermal ? LEG_THERMAL : 0);
+  int rc = SDS_OK;
+  // one setup launch per engine launch (it also rewinds the item counter)
+  auto setup = [&]() -> int {
+    engine_setup_kernel<<<8, 1024, 0, st>>>(group_offset, d->ngroup, d->ntime, d->nspw, d->npol, N,
+                                            P.target_rows, thermal_coef, freq, ws.item_start,
+                                            ws.wl, ws.wr, ws.counter);
+    SDS_LAUNCH_CHECK("engine_setup_kernel");
+    ++g_last_launches;
+    return SDS_OK;
+  };
+  if (pl.math == SDS_F32) {  // one pass over the inputs for every leg
+    if ((rc = setup()) != SDS_OK) return rc;
+    return run_engine<float>(N, P, legs, st);
+  }
+  for (int leg = 1; leg <= 4 && rc == SDS_OK; leg <<= 1)
+    if (legs & leg) {
+      if ((rc = setup()) != SDS_OK) return rc;
+      rc = run_engine<double>(N, P, leg, st);
+    }
+  return rc;
+}
+
+extern "C" int sds_engine_last_launches(void) { return sds::g_last_launches; }

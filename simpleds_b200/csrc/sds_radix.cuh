@@ -14,33 +14,33 @@
 
 namespace sds {
 
-constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
 // radix list of length N: 8s while they fit, then the remaining factor
-constexpr int fft_npass(int N) { return (ilog2(N) + 2) / 3; }
-constexpr int fft_radix(int N, int p) {
+__host__ __device__ constexpr int fft_npass(int N) { return (ilog2(N) + 2) / 3; }
+__host__ __device__ constexpr int fft_radix(int N, int p) {
   int lg = ilog2(N) - 3 * p;
   return lg >= 3 ? 8 : (1 << lg);
 }
-constexpr int fft_ns(int N, int p) {  // product of radices before pass p
+__host__ __device__ constexpr int fft_ns(int N, int p) {  // product of radices before pass p
   int ns = 1;
   for (int i = 0; i < p; ++i) ns *= fft_radix(N, i);
   return ns;
 }
 // twiddle table (one per length): for pass p >= 1, entries [m][q-1][tau]
-constexpr int fft_tw_count(int N, int p) {
+__host__ __device__ constexpr int fft_tw_count(int N, int p) {
   return p == 0 ? 0 : (8 / fft_radix(N, p)) * (fft_radix(N, p) - 1) * (N / 8);
 }
-constexpr int fft_tw_offset(int N, int p) {
+__host__ __device__ constexpr int fft_tw_offset(int N, int p) {
   int off = 0;
   for (int i = 0; i < p; ++i) off += fft_tw_count(N, i);
   return off;
 }
-constexpr int fft_tw_total(int N) { return fft_tw_offset(N, fft_npass(N)); }
-constexpr int fft_pad(int o) { return o + (o >> 3); }
-constexpr int fft_buf_elems(int N) { return N + (N >> 3); }
+__host__ __device__ constexpr int fft_tw_total(int N) { return fft_tw_offset(N, fft_npass(N)); }
+__host__ __device__ constexpr int fft_pad(int o) { return o + (o >> 3); }
+__host__ __device__ constexpr int fft_buf_elems(int N) { return N + (N >> 3); }
 
-constexpr int brev(int i, int bits) {
+__host__ __device__ constexpr int brev(int i, int bits) {
   int r = 0;
   for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b);
   return r;

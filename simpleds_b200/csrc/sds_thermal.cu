@@ -77,7 +77,78 @@ thermal_full_kernel(const void *n1, const void *n2, int ns_dtype, int64_t stride
   }
 }
 
+// Pair sums of the thermal estimate per (group, spw, pol, time) without the B x B
+// array: all = sum_k wl A B + wr A' B', auto = sum_k wl C + wr C' (header comment).
+__global__ void __launch_bounds__(128)
+thermal_avg_kernel(const void *n1, const void *n2, int ns_dtype, int64_t stride_s,
+                   int64_t stride_p, const double *__restrict__ coef,
+                   const double *__restrict__ freq, const double *__restrict__ int_time,
+                   const double *__restrict__ pol_factor, const int32_t *__restrict__ goff, int P,
+                   int T, int F, int SP, double *__restrict__ out_all,
+                   double *__restrict__ out_auto) {
+  __shared__ double red[2][4];
+  const int t = blockIdx.x, sp = blockIdx.y, g = blockIdx.z, s = sp / P, p = sp % P;
+  const int b0 = goff[g], b1 = goff[g + 1];
+  const int64_t base = (int64_t)s * stride_s + (int64_t)p * stride_p;
+  const double *cf = coef + (int64_t)sp * F, *nu = freq + (int64_t)s * F;
+  double all = 0.0, au = 0.0;
+  for (int k = threadIdx.x; k < F - 1; k += blockDim.x) {
+    const double c0 = cf[k], c1 = cf[k + 1];
+    if (!(isfinite(c0) && isfinite(c1))) continue;
+    const double hd = 0.5 * (nu[k + 1] - nu[k]);
+    double A = 0, Ap = 0, Bv = 0, Bp = 0, Cv = 0, Cp = 0;
+    for (int b = b0; b < b1; ++b) {
+      const int64_t o = base + ((int64_t)b * T + t) * F + k;
+      const double tj = int_time[(int64_t)b * T + t];
+      const double it = tj > 0.0 ? 1.0 / tj : 0.0;
+      const double i0 = load_real(n2, ns_dtype, o), i1 = load_real(n2, ns_dtype, o + 1);
+      const double j0 = load_real(n1, ns_dtype, o), j1 = load_real(n1, ns_dtype, o + 1);
+      const bool ei = ns_valid(i0) && ns_valid(i1), ej = ns_valid(j0) && ns_valid(j1);
+      const double l0 = ei ? rsqrt(i0) : 0.0, l1 = ei ? rsqrt(i1) : 0.0;
+      const double r0 = ej ? rsqrt(j0) * it : 0.0, r1 = ej ? rsqrt(j1) * it : 0.0;
+      A += l0; Ap += l1; Bv += r0; Bp += r1; Cv += l0 * r0; Cp += l1 * r1;
+    }
+    all += hd * (c0 * A * Bv + c1 * Ap * Bp);
+    au += hd * (c0 * Cv + c1 * Cp);
+  }
+  for (int m = 16; m > 0; m >>= 1) {
+    all += __shfl_xor_sync(0xffffffffu, all, m);
+    au += __shfl_xor_sync(0xffffffffu, au, m);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = all; red[1][threadIdx.x >> 5] = au; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double f = 1e-6 * pol_factor[p];
+    const int64_t o = ((int64_t)g * SP + sp) * T + t;
+    out_all[o] = f * (red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+    out_auto[o] = f * (red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+  }
+}
+
 }  // namespace sds
+
+extern "C" int sds_thermal_power_avg(const void *n1, const void *n2, int nsample_dtype,
+                                     int64_t stride_s, int64_t stride_p, const double *coef,
+                                     const double *freq, const double *int_time,
+                                     const double *pol_factor, const int32_t *group_offset,
+                                     int ngroup, int S, int P, int B, int T, int F,
+                                     double *out_all, double *out_auto, sds_stream stream) {
+  SDS_CHECK_ARG(n1 && n2 && coef && freq && int_time && pol_factor && group_offset && out_all &&
+                    out_auto, "sds_thermal_power_avg: NULL pointer");
+  SDS_CHECK_ARG(nsample_dtype == SDS_F32 || nsample_dtype == SDS_F64,
+                "sds_thermal_power_avg: nsample dtype must be SDS_F32 or SDS_F64");
+  SDS_CHECK_ARG(S >= 0 && P >= 0 && B >= 0 && T >= 0 && F >= 0 && ngroup >= 0,
+                "sds_thermal_power_avg: negative dimension");
+  SDS_CHECK_ARG((int64_t)S * P <= 65535 && ngroup <= 65535,
+                "sds_thermal_power_avg: S*P or ngroup exceeds 65535");
+  if ((int64_t)S * P * T == 0 || ngroup == 0) return SDS_OK;
+  dim3 grid(T, S * P, ngroup);
+  sds::thermal_avg_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      n1, n2, nsample_dtype, stride_s, stride_p, coef, freq, int_time, pol_factor, group_offset, P,
+      T, F, S * P, out_all, out_auto);
+  SDS_LAUNCH_CHECK("thermal_avg_kernel");
+  return SDS_OK;
+}
 
 extern "C" int sds_thermal_power_full(const void *n1, const void *n2, int nsample_dtype,
                                       int64_t stride_s, int64_t stride_p, const double *coef,

@@ -1,0 +1,248 @@
+"""Batched multi-group front end of the fused path.
+
+The reference handles one redundant group per ``DelaySpectrum`` object and the
+caller loops over groups (ds.py:891-900) and averages the (Nbls, Nbls) power
+tensor afterwards (tutorial cell 41).  ``RedundantPipeline`` takes a whole array
+at once -- visibilities (Npols, Nbls, Ntimes, Nchan) with baselines sorted by
+redundant group -- and returns, per group / spectral window / polarisation /
+delay, the mean over baseline pairs and times of the data power, of the power of
+a matching noise realisation, and of the thermal estimate, i.e. what
+``select_spectral_windows -> generate_noise -> calculate_delay_spectrum ->
+mean`` gives per group.  One call of ``sds_engine_run`` (include/sds.h) does the
+work for power-of-two windows; other lengths go through the unfused kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from scipy.signal import windows
+
+from . import _lib, ops
+from ._lib import SDS_F32, SDS_F64, EngineDesc, check, ptr, stream_ptr
+
+C_M_PER_S = 299792458.0
+K_B_J_PER_K = 1.380649e-23
+
+
+def radiometer_tables(freq_hz, trcvr_k, beam_area_sr, polarization_array, taper_values, delta_f):
+    """Per-channel factors of the noise model, evaluated once on the host.
+
+    freq_hz (S,N), trcvr_k (S,N), beam_area_sr (S,P,N).  Returns
+    sigma_coef (S,P,N) [ds.py:3546-3581 without the per-sample 1/sqrt(t n)],
+    thermal_coef (S,P,N) [ds.py:3668-3699 channel part], pol_factor (P,)."""
+    freq_hz = np.asarray(freq_hz, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        tsys = 180.0 * np.power(freq_hz * 1e-9 / 0.18, -2.55) + np.asarray(trcvr_k, dtype=np.float64)
+        jy2mk = 1e-23 * C_M_PER_S**2 / (2.0 * freq_hz**2 * K_B_J_PER_K)
+        amp = tsys[:, None, :] * 1e3 * np.asarray(beam_area_sr, dtype=np.float64)
+        sigma_coef = amp / np.sqrt(delta_f) / jy2mk[:, None, :]
+        thermal_coef = amp**2 * np.asarray(taper_values, dtype=np.float64) ** 2 * freq_hz[:, None, :] ** 4
+        thermal_coef = np.where(np.isfinite(amp), thermal_coef, np.nan)
+    npol = np.array([2 if p in np.arange(1, 5) else 1 for p in polarization_array])
+    return sigma_coef, thermal_coef, 1.0 / (npol * np.sqrt(2))
+
+
+class RedundantPipeline:
+    """See module docstring.
+
+    Parameters: ``freq_hz`` (Nchan,) channel frequencies; ``spectral_windows`` list of
+    (start, end) inclusive channel ranges of equal length (ds.py:3243-3264);
+    ``group_offset`` (Ngroups+1,) rising baseline offsets of the redundant groups;
+    ``trcvr_k`` scalar or (Nchan,); ``beam_area_sr`` scalar, (Nchan,) or (Npols, Nchan);
+    ``precision`` "complex64" (fp32 math) or "complex128" (fp64 math)."""
+
+    def __init__(self, freq_hz, spectral_windows, polarization_array, group_offset, trcvr_k,
+                 beam_area_sr, taper=None, precision="complex64", seed=0, device=None):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.taper = windows.blackmanharris if taper is None else taper
+        if not callable(self.taper):
+            raise ValueError(
+                "Input spectral taper must be a function or callable whose arguments are "
+                "the length of the band over which Fourier Transform is taken."
+            )
+        if precision not in ("complex64", "complex128"):
+            raise ValueError("precision must be 'complex128' or 'complex64'")
+        self.precision, self.seed = precision, int(seed)
+        self.math = SDS_F64 if precision == "complex128" else SDS_F32
+        freq_hz = np.asarray(freq_hz, dtype=np.float64).reshape(-1)
+        self.nchan = freq_hz.size
+        sw = np.asarray(spectral_windows, dtype=np.int64).reshape(-1, 2)
+        nf = sw[:, 1] + 1 - sw[:, 0]
+        if not np.all(nf == nf[0]):
+            raise ValueError("Spectral windows must all have the same size.")
+        if sw.min() < 0 or sw[:, 1].max() >= self.nchan:
+            raise IndexError("spectral window channel index out of range")
+        self.win_start = [int(x) for x in sw[:, 0]]
+        self.nspw, self.nfreq = sw.shape[0], int(nf[0])
+        self.polarization_array = np.asarray(polarization_array, dtype=np.int64)
+        self.npol = self.polarization_array.size
+        go = np.asarray(group_offset, dtype=np.int64)
+        if go.ndim != 1 or go.size < 2 or go[0] != 0 or np.any(np.diff(go) < 0):
+            raise ValueError("group_offset must rise from 0 to Nbls")
+        self.group_offset_host = go
+        self.ngroup, self.nbl = go.size - 1, int(go[-1])
+        self.group_sizes = np.diff(go)
+        chans = sw[:, 0, None] + np.arange(self.nfreq)
+        self.freq_windows = freq_hz[chans]  # (S, N)
+        # delta_x of the transform is the FIRST window's channel width (ds.py:3502)
+        self.delta_f = float(self.freq_windows[0, 1] - self.freq_windows[0, 0]) if self.nfreq > 1 else 1.0
+        trcvr = np.broadcast_to(np.asarray(trcvr_k, dtype=np.float64), (self.nchan,))[chans]
+        beam = np.broadcast_to(np.asarray(beam_area_sr, dtype=np.float64), (self.npol, self.nchan))
+        beam = np.transpose(beam[:, chans], (1, 0, 2))  # (S, P, N)
+        self.taper_values = np.asarray(self.taper(self.nfreq), dtype=np.float64)
+        sc, tc, pf = radiometer_tables(self.freq_windows, trcvr, beam, self.polarization_array,
+                                       self.taper_values, self.delta_f)
+        dev = self.device
+        self.sigma_coef64 = torch.as_tensor(sc, device=dev)
+        self.sigma_coef32 = torch.as_tensor(np.nan_to_num(sc, nan=np.inf, posinf=np.inf).astype(np.float32), device=dev)
+        self.thermal_coef = torch.as_tensor(tc, device=dev)
+        self.pol_factor = torch.as_tensor(pf, device=dev)
+        self.freq_dev = torch.as_tensor(self.freq_windows, device=dev)
+        self.group_offset = torch.as_tensor(go.astype(np.int32), device=dev)
+        self.delay_array_ns = np.fft.fftshift(np.fft.fftfreq(self.nfreq, d=self.delta_f)) * 1e9
+        self.plan = ops.get_plan(self.nfreq, self.math, self.taper)
+        self.fused = self._fused_ok()
+        self.kernel_launches = 0
+        self.reset()
+
+    def _fused_ok(self):
+        n = self.nfreq
+        return (n & (n - 1)) == 0 and 64 <= n <= 2048 and self.nchan % 16 == 0 and \
+            all(w % 16 == 0 for w in self.win_start)
+
+    def reset(self):
+        dev, shape = self.device, (self.ngroup, self.nspw, self.npol, self.nfreq)
+        self.pow_all = torch.zeros(shape, dtype=torch.complex128, device=dev)
+        self.pow_auto = torch.zeros(shape, dtype=torch.complex128, device=dev)
+        self.noise_all = torch.zeros(shape, dtype=torch.complex128, device=dev)
+        self.noise_auto = torch.zeros(shape, dtype=torch.complex128, device=dev)
+        self.thermal_all = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
+        self.thermal_auto = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
+        self.ntimes_done = 0
+        self._ws = None
+
+    # ------------------------------------------------------------------ one batch
+    def process(self, vis, flags, nsample, int_time, time_offset=0, ntime_total=None, noise="philox",
+                thermal=True, noise_in=None):
+        """Accumulate one batch of times.  vis complex64 (P,B,T,Nchan); flags bool/uint8
+        and nsample float32 of the same shape; int_time float32 (B,T).  ``noise``:
+        "philox" (in-kernel realisation), None, or "inject" with ``noise_in`` (a
+        frequency-domain noise array shaped like vis; parity tests)."""
+        P, B, T, F0 = vis.shape
+        if (P, B, F0) != (self.npol, self.nbl, self.nchan):
+            raise ValueError(f"vis has shape {tuple(vis.shape)}, expected ({self.npol}, {self.nbl}, T, {self.nchan})")
+        if tuple(flags.shape) != tuple(vis.shape) or tuple(nsample.shape) != tuple(vis.shape) \
+                or tuple(int_time.shape) != (B, T):
+            raise ValueError("flags/nsample must match vis and int_time must be (Nbls, Ntimes)")
+        if vis.dtype != torch.complex64 or nsample.dtype != torch.float32 or int_time.dtype != torch.float32:
+            raise ValueError("vis must be complex64, nsample and int_time float32")
+        fl = flags.view(torch.uint8) if flags.dtype == torch.bool else flags
+        if fl.dtype != torch.uint8:
+            raise ValueError("flags must be bool or uint8")
+        vis, fl, nsample, int_time = vis.contiguous(), fl.contiguous(), nsample.contiguous(), int_time.contiguous()
+        mode = {None: 0, "philox": 1, "inject": 2}[noise]
+        if mode == 2:
+            if noise_in is None or tuple(noise_in.shape) != tuple(vis.shape) or noise_in.dtype != torch.complex64:
+                raise ValueError("noise='inject' needs noise_in complex64 shaped like vis")
+            noise_in = noise_in.contiguous()
+        ntot = T if ntime_total is None else int(ntime_total)
+        if self.fused:
+            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
+        else:
+            self._process_unfused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
+        self.ntimes_done += T
+
+    def _process_fused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot):
+        lib = _lib.load()
+        P, B, T, F0 = vis.shape
+        d = EngineDesc()
+        d.npol, d.nbl, d.ntime, d.nchan = P, B, T, F0
+        d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, self.ngroup, 1, mode
+        for i, w in enumerate(self.win_start):
+            d.win_start[i] = w
+        d.time_offset, d.ntime_total, d.bl_offset, d.nbl_total = int(time_offset), ntot, 0, B
+        d.seed, d.delta_f = self.seed, self.delta_f
+        need = lib.sds_engine_workspace_bytes(self.plan.handle, C.byref(d))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+        rc = lib.sds_engine_run(
+            self.plan.handle, C.byref(d), ptr(vis), ptr(fl), ptr(nsample), ptr(int_time),
+            ptr(self.group_offset), ptr(self.sigma_coef32), ptr(self.thermal_coef if thermal else None),
+            ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all.view(torch.float64)),
+            ptr(self.pow_auto.view(torch.float64)), ptr(self.noise_all.view(torch.float64)),
+            ptr(self.noise_auto.view(torch.float64)), ptr(self.thermal_all), ptr(self.thermal_auto),
+            ptr(self._ws), stream_ptr(),
+        )
+        check(rc, "sds_engine_run")
+        self.kernel_launches += lib.sds_engine_last_launches()
+
+    def _process_unfused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot):
+        """Any window length / alignment: the API-level kernels chained on device
+        (delay transform with window origins -> pair sums; sigma -> draw -> transform)."""
+        P, B, T, F0 = vis.shape
+        S, N = self.nspw, self.nfreq
+        x = ops.delay_transform(self.plan, vis, fl, self.delta_f, win_start=self.win_start)  # (S,P,B,T,N)
+        s_all, s_auto = ops.cross_power_sums(x, group_offset=self.group_offset_host)
+        self.pow_all += s_all.sum(dim=3)
+        self.pow_auto += s_auto.sum(dim=3)
+        self.kernel_launches += 2
+        chans = np.asarray(self.win_start)[:, None] + np.arange(N)
+        ns_w = ops.take_windows(nsample[None], chans)  # (S,P,B,T,N)
+        self.kernel_launches += 1
+        it64 = int_time.to(torch.float64)
+        if mode:
+            fl_w = ops.take_windows(fl[None], chans)
+            if mode == 1:
+                sig = ops.noise_sigma(self.sigma_coef64, it64, ns_w[:, None])
+                # one Philox stream per batch (the fused path's stream is keyed by
+                # global sample coordinates instead; both are valid realisations)
+                off = int(time_offset) * S * P * B * N
+                nz = ops.generate_noise(sig[:, 0], seed=self.seed, offset=off, out_dtype=x.dtype)
+                self.kernel_launches += 2
+            else:
+                nz = ops.take_windows(noise_in[None], chans)
+                self.kernel_launches += 1
+            xn = ops.delay_transform(self.plan, nz, fl_w, self.delta_f)
+            n_all, n_auto = ops.cross_power_sums(xn, group_offset=self.group_offset_host)
+            self.noise_all += n_all.sum(dim=3)
+            self.noise_auto += n_auto.sum(dim=3)
+            self.kernel_launches += 3
+        if thermal:
+            t_all, t_auto = ops.thermal_power_sums(ns_w, ns_w, self.thermal_coef, self.freq_dev, it64,
+                                                   self.pol_factor, self.group_offset_host)
+            self.thermal_all += t_all.sum(dim=3)
+            self.thermal_auto += t_auto.sum(dim=3)
+            self.kernel_launches += 1
+
+    # ------------------------------------------------------------------ results
+    def sums(self):
+        """Raw accumulators (what ranks reduce over NVLink)."""
+        return dict(pow_all=self.pow_all, pow_auto=self.pow_auto, noise_all=self.noise_all,
+                    noise_auto=self.noise_auto, thermal_all=self.thermal_all,
+                    thermal_auto=self.thermal_auto)
+
+    def result(self, ntimes=None):
+        """Means over ordered baseline pairs and times, per (group, spw, pol[, delay]).
+
+        ``*_all``: every ordered pair (i, j), autos included (tutorial cell 41);
+        ``*_noautos``: i != j (utils.remove_auto_correlations); NaN for 1-baseline groups."""
+        T = self.ntimes_done if ntimes is None else ntimes
+        n = torch.as_tensor(self.group_sizes, dtype=torch.float64, device=self.device)
+        n4, n3 = n.view(-1, 1, 1, 1), n.view(-1, 1, 1)
+        out = {}
+        for key, a, b in (("power", self.pow_all, self.pow_auto), ("noise_power", self.noise_all, self.noise_auto)):
+            out[key + "_all"] = a / (n4 * n4 * T)
+            out[key + "_noautos"] = (a - b) / (n4 * (n4 - 1) * T)
+        out["thermal_all"] = self.thermal_all / (n3 * n3 * T)
+        out["thermal_noautos"] = (self.thermal_all - self.thermal_auto) / (n3 * (n3 - 1) * T)
+        out["delay_array_ns"] = self.delay_array_ns
+        return out
+
+    # work and byte counts used by bench.py
+    def pair_spectra(self, ntimes):
+        return int((self.group_sizes.astype(np.int64) ** 2).sum()) * self.nspw * self.npol * int(ntimes)
+
+    def algorithmic_bytes(self, ntimes):
+        distinct = len(set(c for w in self.win_start for c in range(w, w + self.nfreq)))
+        return 13 * self.npol * self.nbl * int(ntimes) * distinct

@@ -239,3 +239,38 @@ def thermal_power_full(n1, n2, coef, freq, int_time, pol_factor):
         "sds_thermal_power_full",
     )
     return out
+
+
+def thermal_power_sums(n1, n2, coef, freq, int_time, pol_factor, group_offset=None):
+    """Pair sums of the thermal estimate (sds_thermal_power_avg): returns
+    (sum_all, sum_auto), each f64 (G,S,P,T)."""
+    _lib.require_cuda()
+    if tuple(n1.shape) != tuple(n2.shape):
+        raise ValueError("nsample_1 and nsample_2 must have same shape")
+    if n2.dtype != n1.dtype:
+        n2 = n2.to(n1.dtype)
+    n1, ss1, sp1 = _sp_strides(n1)
+    n2, ss2, sp2 = _sp_strides(n2)
+    if (ss1, sp1) != (ss2, sp2):
+        n1, n2 = n1.contiguous(), n2.contiguous()
+        ss1, sp1 = n1.stride()[0], n1.stride()[1]
+    S, P, B, T, F = n1.shape
+    dev = n1.device
+    coef = torch.as_tensor(coef, dtype=torch.float64, device=dev).contiguous()
+    freq = torch.as_tensor(freq, dtype=torch.float64, device=dev).contiguous()
+    it = torch.as_tensor(int_time, dtype=torch.float64, device=dev).contiguous()
+    pf = torch.as_tensor(pol_factor, dtype=torch.float64, device=dev).contiguous()
+    if group_offset is None:
+        group_offset = [0, B]
+    go = np.asarray(group_offset, dtype=np.int64)
+    G = go.size - 1
+    god = torch.as_tensor(go.astype(np.int32), device=dev)
+    out_all = torch.empty((G, S, P, T), dtype=torch.float64, device=dev)
+    out_auto = torch.empty_like(out_all)
+    check(
+        _lib.load().sds_thermal_power_avg(ptr(n1), ptr(n2), real_dtype_code(n1), ss1, sp1, ptr(coef),
+                                          ptr(freq), ptr(it), ptr(pf), ptr(god), G, S, P, B, T, F,
+                                          ptr(out_all), ptr(out_auto), stream_ptr()),
+        "sds_thermal_power_avg",
+    )
+    return out_all, out_auto
