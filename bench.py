@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the delay-spectrum hot path (BASELINE.json metric: delay-spectrum
+baseline-pairs/sec; achieved HBM GB/s vs peak).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference CPU path (oracle port)
+
+A step = one pass of the fused path over one HBM-resident batch of the synthetic
+HERA-350 array (BASELINE.json configs[2]: 350 antennas -> 61 075 baselines in
+3 601 redundant groups, 1024 channels in 4 spectral windows of 256, 4 pols,
+Blackman-Harris taper): window select + flag mask + taper + delay transform of the
+data and of an in-kernel noise realisation, pair sums and thermal sums, for every
+group, of `--times` integrations.  The 1000-time job is streamed as such batches;
+with N GPUs each rank takes its own times (weak scaling) and one NCCL reduce of
+the partial sums closes the job.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "delay-spectrum baseline-pairs/sec"
+UNIT = "pair-spectra/s"
+
+CONFIGS = {
+    # name: (array, nchan, nwin, npol, f0, df, t_int)
+    "hera350": dict(array="hera_350", nchan=1024, nwin=4, npol=4, f0=100e6, df=97656.25, t_int=10.7,
+                    pols=[-5, -6, -7, -8], seed=1003),
+    "paper64": dict(array="paper_grid", nchan=208, nwin=1, npol=2, f0=100e6, df=492610.84375, t_int=42.95,
+                    pols=[1, 2], seed=1002),
+    "ska512": dict(array="ska_512", nchan=2048, nwin=1, npol=2, f0=50e6, df=146484.375, t_int=0.85,
+                   pols=[-5, -6], seed=1005),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_sample_inputs(cfg, n, ntime, seed=0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    P, F = cfg["npol"], cfg["nchan"]
+    shape = (1, 1, P, n, ntime, F)
+    common = rng.standard_normal((1, 1, P, 1, ntime, F)) + 1j * rng.standard_normal((1, 1, P, 1, ntime, F))
+    vis = (30 * common + rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    flags = rng.random(shape) < 0.06
+    ns = rng.integers(32, 61, shape).astype(np.float64)
+    freq = (cfg["f0"] + cfg["df"] * np.arange(F))[None]
+    N = F // cfg["nwin"]
+    wins = [(w * N, (w + 1) * N - 1) for w in range(cfg["nwin"])]
+    return dict(vis=vis, flags=flags, nsample=ns, freq_array_hz=freq, trcvr_k=np.full((1, F), 144.0),
+                beam_area_sr=np.full((1, P, F), 0.76), integration_time_s=np.full((n, ntime), cfg["t_int"]),
+                polarization_array=np.array(cfg["pols"]), spectral_windows=wins)
+
+
+def _cpu_chunk(args):
+    """One time-chunk of the reference path (the reference's tests show time slices
+    commute, test_io.py:570-631): windows -> noise -> transform -> cross multiply ->
+    thermal -> mean over pairs and time, all via the oracle restatement."""
+    from oracle import simpleds_oracle as orc
+
+    pr, sl, seed = args
+    q = dict(pr)
+    for k in ("vis", "flags", "nsample"):
+        q[k] = pr[k][..., sl, :]
+    q["integration_time_s"] = pr["integration_time_s"][:, sl]
+    res = orc.pipeline_reference(**q, noise_seed=seed)
+    out = [orc.average_power(res[k], remove_autos=True) for k in ("power_array", "noise_power")]
+    out.append(res["thermal_power"].mean(axis=(2, 3, 4)))
+    return [np.asarray(o) for o in out]
+
+
+def cpu_reference_rate(cfg, n, ntime, procs):
+    """pair-spectra/s of the reference CPU path on one group of n baselines."""
+    pr = _cpu_sample_inputs(cfg, n, ntime)
+    chunks = np.array_split(np.arange(ntime), max(1, min(procs, ntime)))
+    jobs = [(pr, slice(int(c[0]), int(c[-1]) + 1), i) for i, c in enumerate(chunks) if len(c)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            pool.map(_cpu_chunk, jobs)
+    else:
+        for j in jobs:
+            _cpu_chunk(j)
+    dt = time.perf_counter() - t0
+    pairs = n * n * cfg["nwin"] * cfg["npol"] * ntime
+    return pairs / dt, dt
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n, ntime = args.cpu_bl, max(cores, args.cpu_times)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(cfg, n, ntime, cores)
+    rates, times = [], []
+    for _ in range(max(1, min(args.steps, 8))):
+        r, dt = cpu_reference_rate(cfg, n, ntime, cores)
+        rates.append(r)
+        times.append(dt)
+    value = float(np.sum([n * n * cfg["nwin"] * cfg["npol"] * ntime] * len(times)) / np.sum(times))
+    sample = (f"one redundant group of {n} baselines x {cfg['npol']} pols x {cfg['nwin']} windows of "
+              f"{cfg['nchan'] // cfg['nwin']} ch x {ntime} times per step, split over {cores} processes by time; "
+              "oracle port of the reference's numpy path incl. noise draw, thermal estimate and the mean")
+    line = dict(
+        impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times),
+        warmup=min(args.warmup, 1), ms_per_step=1e3 * float(np.mean(times)), higher_is_better=True,
+        scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=workload_config(args, cfg, None),
+        cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+        e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+    )
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, pipe):
+    c = dict(
+        workload=f"{args.config}: synthetic {cfg['array']} redundant array, {cfg['nchan']} channels in "
+                 f"{cfg['nwin']} spectral windows, {cfg['npol']} pols, Blackman-Harris taper, "
+                 f"{args.times} times per step per GPU (streamed batches of the 1000-time job), "
+                 "delay transform + noise realisation + redundant pair average + thermal estimate",
+        times_per_step_per_gpu=args.times, precision=args.precision,
+        l2_policy="inputs larger than L2 (no flush needed)",
+    )
+    if pipe is not None:
+        c.update(nbls=pipe.nbl, ngroups=pipe.ngroup, nfreq=pipe.nfreq, nspw=pipe.nspw)
+    return c
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+        self.path = tempfile.mktemp(prefix="sds_clocks_", suffix=".csv")
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def run_gpu_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from simpleds_b200 import synth
+    from simpleds_b200.engine import RedundantPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lattice, basis = getattr(synth, cfg["array"])()
+    red = synth.redundant_groups(lattice, basis)
+    F, N = cfg["nchan"], cfg["nchan"] // cfg["nwin"]
+    freq = cfg["f0"] + cfg["df"] * np.arange(F)
+    wins = [(w * N, (w + 1) * N - 1) for w in range(cfg["nwin"])]
+    pipe = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                             precision=args.precision, seed=0)
+    T = args.times
+    ntime_total = 1000
+    # this rank's resident batch (generation is not timed)
+    vis, flags, nsample, int_time = synth.make_visibilities(
+        red["group_offset"], cfg["npol"], T, freq, seed=cfg["seed"], device=dev, t_int=cfg["t_int"],
+        time_offset=rank * T)
+    torch.cuda.synchronize()
+
+    def step(i):
+        # step i of this rank covers global times [(i*world + rank) * T, ...)
+        toff = ((i * world + rank) * T) % max(ntime_total - T + 1, 1)
+        pipe.process(vis, flags, nsample, int_time, time_offset=toff, ntime_total=ntime_total,
+                     noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
+
+    def job_reduce():
+        if world > 1:
+            for t in pipe.sums().values():
+                dist.reduce(t.view(torch.float64) if t.is_complex() else t, dst=0, op=dist.ReduceOp.SUM)
+
+    for i in range(args.warmup):
+        step(i)
+    job_reduce()
+    torch.cuda.synchronize()
+    pipe.reset()
+    launches0 = pipe.kernel_launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    ev[0].record()
+    for i in range(args.steps):
+        ev[1 + 2 * i].record()
+        step(i)
+        ev[2 + 2 * i].record()
+    job_reduce()
+    ev[-1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[1 + 2 * i].elapsed_time(ev[2 + 2 * i]) for i in range(args.steps)]
+    if world > 1:
+        tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms = float(tmax.item())
+    launches = pipe.kernel_launches - launches0
+    pairs_per_step = pipe.pair_spectra(T)
+    value = pairs_per_step * args.steps * world / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (the fused engine launch; the tiny setup launch that
+    # precedes it is inside the same event pair)
+    peak, peak_src = peaks()
+    alg_bytes = pipe.algorithmic_bytes(T)
+    kern_ms = float(np.mean(step_ms))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=None, peak_source=peak_src, bytes_per_launch=alg_bytes,
+                    kernel_ms=kern_ms, kernel="sds::engine_kernel (+ engine_setup_kernel)")
+
+    line = None
+    if rank == 0:
+        res = pipe.result(ntimes=args.steps * T)
+        finite = bool(torch.isfinite(res["power_all"].real).all().item())
+        # end to end through the public API with pinned HOST buffers (H2D + D2H timed)
+        e2e = run_e2e(args, cfg, pipe, red, freq, dev) if not args.no_e2e else None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            r, dt = cpu_reference_rate(cfg, args.cpu_bl, args.cpu_times, 1)
+            cpu = dict(value=r, unit=UNIT, cores=1, kind="port", seconds=dt,
+                       sample=f"one redundant group of {args.cpu_bl} baselines x {cfg['npol']} pols x "
+                              f"{cfg['nwin']} windows of {N} ch x {args.cpu_times} times, single process "
+                              "(the reference's numpy path is single-threaded); oracle port incl. noise "
+                              "draw, thermal estimate and the mean over pairs/time")
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32" if args.precision == "complex64" else "f64", data="synthetic",
+            config=workload_config(args, cfg, pipe), roofline=roofline, cpu_baseline=cpu, e2e=e2e,
+            gpu_launches=int(launches), clocks=clocks, outputs_finite=finite,
+            input_gb_per_step_per_gpu=alg_bytes / 1e9,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_e2e(args, cfg, pipe, red, freq, dev):
+    """Same metric through RedundantPipeline.process_host: pinned host arrays in, host
+    results out, every step."""
+    import torch
+
+    from simpleds_b200 import synth
+
+    Te = max(1, min(args.e2e_times, args.times))
+    vis, flags, nsample, int_time = synth.make_visibilities(
+        red["group_offset"], cfg["npol"], Te, freq, seed=cfg["seed"] + 1, device=dev, t_int=cfg["t_int"])
+    host = [t.cpu().pin_memory() for t in (vis, flags, nsample, int_time)]
+    del vis, flags, nsample, int_time
+    torch.cuda.empty_cache()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    out = None
+    for _ in range(2):
+        pipe.reset()
+        out = pipe.process_host(*host, noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pipe.reset()
+        out = pipe.process_host(*host, noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    d2h = sum(v.nbytes for v in out.values() if hasattr(v, "nbytes"))
+    return dict(value=pipe.pair_spectra(Te) / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt, times_per_step=Te, steps=steps,
+                note="pinned host buffers -> H2D -> fused engine -> D2H of the per-group means")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="hera350", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="complex64", choices=["complex64", "complex128"])
+    ap.add_argument("--times", type=int, default=8, help="integrations per step per GPU")
+    ap.add_argument("--e2e-times", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-bl", type=int, default=64)
+    ap.add_argument("--cpu-times", type=int, default=16)
+    ap.add_argument("--no-noise", action="store_true")
+    ap.add_argument("--no-thermal", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3  # timing hygiene: at least 3 warm-up steps
+        run_gpu_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

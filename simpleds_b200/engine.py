@@ -39,7 +39,9 @@ def radiometer_tables(freq_hz, trcvr_k, beam_area_sr, polarization_array, taper_
         thermal_coef = amp**2 * np.asarray(taper_values, dtype=np.float64) ** 2 * freq_hz[:, None, :] ** 4
         thermal_coef = np.where(np.isfinite(amp), thermal_coef, np.nan)
     npol = np.array([2 if p in np.arange(1, 5) else 1 for p in polarization_array])
-    return sigma_coef, thermal_coef, 1.0 / (npol * np.sqrt(2))
+    # numpy keeps the (transposed) memory order of its inputs: the device tables must be C-ordered
+    return (np.ascontiguousarray(sigma_coef), np.ascontiguousarray(thermal_coef),
+            np.ascontiguousarray(1.0 / (npol * np.sqrt(2))))
 
 
 class RedundantPipeline:
@@ -94,11 +96,12 @@ class RedundantPipeline:
         sc, tc, pf = radiometer_tables(self.freq_windows, trcvr, beam, self.polarization_array,
                                        self.taper_values, self.delta_f)
         dev = self.device
-        self.sigma_coef64 = torch.as_tensor(sc, device=dev)
-        self.sigma_coef32 = torch.as_tensor(np.nan_to_num(sc, nan=np.inf, posinf=np.inf).astype(np.float32), device=dev)
-        self.thermal_coef = torch.as_tensor(tc, device=dev)
-        self.pol_factor = torch.as_tensor(pf, device=dev)
-        self.freq_dev = torch.as_tensor(self.freq_windows, device=dev)
+        sc32 = np.ascontiguousarray(np.nan_to_num(sc, nan=np.inf, posinf=np.inf), dtype=np.float32)
+        self.sigma_coef64 = torch.as_tensor(sc, device=dev).contiguous()
+        self.sigma_coef32 = torch.as_tensor(sc32, device=dev).contiguous()
+        self.thermal_coef = torch.as_tensor(tc, device=dev).contiguous()
+        self.pol_factor = torch.as_tensor(pf, device=dev).contiguous()
+        self.freq_dev = torch.as_tensor(np.ascontiguousarray(self.freq_windows), device=dev).contiguous()
         self.group_offset = torch.as_tensor(go.astype(np.int32), device=dev)
         self.delay_array_ns = np.fft.fftshift(np.fft.fftfreq(self.nfreq, d=self.delta_f)) * 1e9
         self.plan = ops.get_plan(self.nfreq, self.math, self.taper)
@@ -214,6 +217,32 @@ class RedundantPipeline:
             self.thermal_all += t_all.sum(dim=3)
             self.thermal_auto += t_auto.sum(dim=3)
             self.kernel_launches += 1
+
+    def process_host(self, vis, flags, nsample, int_time, **kw):
+        """``process`` for HOST arrays (numpy or CPU torch tensors, ideally pinned):
+        uploads them, runs the batch and returns ``result()`` as numpy arrays."""
+        dev = self.device
+        if not hasattr(self, "_stage"):
+            self._stage = {}
+        ins = []
+        for name, a, dt in (("vis", vis, torch.complex64), ("flags", flags, torch.uint8),
+                            ("nsample", nsample, torch.float32), ("int_time", int_time, torch.float32)):
+            t = torch.as_tensor(a)
+            if t.dtype == torch.bool:
+                t = t.view(torch.uint8)
+            if t.dtype != dt:
+                raise ValueError(f"{name} must be {dt}")
+            buf = self._stage.get(name)
+            if buf is None or tuple(buf.shape) != tuple(t.shape):
+                buf = self._stage[name] = torch.empty(t.shape, dtype=dt, device=dev)
+            buf.copy_(t, non_blocking=True)
+            ins.append(buf)
+        self.process(*ins, **kw)
+        res = self.result()
+        out = {}
+        for k, v in res.items():
+            out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+        return out
 
     # ------------------------------------------------------------------ results
     def sums(self):

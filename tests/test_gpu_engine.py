@@ -121,8 +121,13 @@ def test_fused_engine_time_batches_and_shards_are_invariant(cuda_device):
     wins = [(0, 255)]
     _, whole = run_pipeline(a, wins, "complex64", "philox")
     _, parts = run_pipeline(a, wins, "complex64", "philox", batches=[(0, 2), (2, 3), (3, 6)])
-    for key in ("power_all", "power_noautos", "noise_power_all", "noise_power_noautos", "thermal_all"):
-        np.testing.assert_allclose(parts[key], whole[key], rtol=2e-6, atol=0, err_msg=key)
+    # fp32 partial sums are grouped differently; the no-autos mean is a difference of
+    # sums ~n times larger, so the criterion is norm-wise over the delay row
+    for key in ("power_all", "noise_power_all"):
+        assert_close(parts[key], whole[key], 2e-6, what=key)
+    for key in ("power_noautos", "noise_power_noautos"):
+        assert_close(parts[key], whole[key], 2e-5, what=key)
+    np.testing.assert_allclose(parts["thermal_all"], whole["thermal_all"], rtol=2e-6)
 
 
 def test_fused_engine_large_group_and_many_items(cuda_device):
