@@ -35,7 +35,7 @@ def build_lib(force=False, verbose=False):
     """Compile every CUDA source into simpleds_b200/libsds.so; returns its path."""
     if not force and not needs_build():
         return LIB
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("SDS_NVCC_FLAGS", "").split()
     objs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))

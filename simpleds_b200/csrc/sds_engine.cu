@@ -24,6 +24,9 @@
 namespace sds {
 
 constexpr int ENG_STAGES = 3;
+#ifndef ENG_MINBLOCKS
+#define ENG_MINBLOCKS 1
+#endif
 constexpr int LEG_DATA = 1, LEG_NOISE = 2, LEG_THERMAL = 4;
 
 struct EngineParams {
@@ -178,11 +181,13 @@ template <typename T, int N> struct EngCfg {
 };
 
 template <typename T, int N, int LEGS>
-__global__ void __launch_bounds__(EngCfg<T, N>::THREADS)
+__global__ void __launch_bounds__(EngCfg<T, N>::THREADS, ENG_MINBLOCKS)
 engine_kernel(const __grid_constant__ EngineParams P) {
   using C = EngCfg<T, N>;
   constexpr int TPR = C::TPR, WORKER = C::WORKER, ROWS = C::ROWS;
   constexpr bool SAME = sizeof(T) == sizeof(float);
+  constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
+                 HAS_T = (LEGS & LEG_THERMAL) != 0;
   extern __shared__ __align__(128) unsigned char smem[];
 
   // twiddle tables -> shared memory (conflict-free [m][q][tau] layout)
@@ -207,19 +212,17 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   }
   __syncthreads();
 
-  // per-thread constants: taper * delta_f at this thread's 8 channels
+  // per-thread constants: taper * delta_f at this thread's 8 transform channels
   T tapdf[8];
-  float tapdf_f[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < 8; ++r)
     tapdf[r] = reinterpret_cast<const T *>(P.taper)[tau + TPR * r] * (T)P.delta_f;
-    tapdf_f[r] = P.taper_f[tau + TPR * r] * (float)P.delta_f;
-  }
   const int total_items = P.item_start[P.ngroup];
-  const int row_bytes = ((LEGS & LEG_DATA) ? 8 * N : 0) +
-                        ((LEGS & (LEG_NOISE | LEG_THERMAL)) ? 4 * N : 0) +
-                        ((LEGS & (LEG_DATA | LEG_NOISE)) ? N : 0);
-  uint32_t gstep = 0;  // steps consumed by this worker since kernel start (slot/parity)
+  constexpr int ROW_BYTES = (HAS_D ? 8 * N : 0) + ((HAS_N || HAS_T) ? 4 * N : 0) +
+                            ((HAS_D || HAS_N) ? N : 0);
+  const int64_t row_stride = (int64_t)P.ntime * P.nchan;  // samples between baselines
+  uint32_t slot_c = 0, par_c = 0;  // consumer ring position / phase parity
+  uint32_t slot_p = 0;             // producer ring position
   __shared__ int item_bcast[C::NWORKER];
 
   for (;;) {
@@ -247,30 +250,44 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     const int tc = local % nchunks, sp = local / nchunks, p = sp % P.npol, s = sp / P.npol;
     const int t0 = tc * chunk, t1 = min(P.ntime, t0 + chunk);
     const int steps_per_t = (ng + ROWS - 1) / ROWS, nsteps = (t1 - t0) * steps_per_t;
-    const int wstart = P.win_start[s];
+    // sample offset of (pol p, first baseline of the group, time t0, window start)
+    const int64_t e00 = (((int64_t)p * P.nbl + b0) * P.ntime + t0) * P.nchan + P.win_start[s];
 
-    // producer: lane 0 stages step k (rows i0 .. i0+ROWS-1 of time t)
-    auto issue = [&](int k) {
-      if (wl != 0) return;
-      const uint32_t slot = (gstep + (uint32_t)k) % ENG_STAGES;
-      const int t = t0 + k / steps_per_t, i0 = (k % steps_per_t) * ROWS;
-      const int nact = min(ROWS, ng - i0);
-      mbar_expect_tx(&full[slot], (uint32_t)(nact * row_bytes));
-      for (int rr = 0; rr < nact; ++rr) {
-        const int64_t e = (((int64_t)p * P.nbl + b0 + i0 + rr) * P.ntime + t) * P.nchan + wstart;
-        unsigned char *dst = stages + slot * C::SLOT + rr * C::ROWB;
-        if (LEGS & LEG_DATA) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot]);
-        if (LEGS & (LEG_NOISE | LEG_THERMAL)) tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot]);
-        if (LEGS & (LEG_DATA | LEG_NOISE)) tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot]);
+    // ---- producer state (lane 0 stages rows i0 .. i0+ROWS-1 of time t) ----------
+    int pi0 = 0;          // first row of the next step to stage
+    int64_t pe = e00;     // its sample offset
+    int64_t pe_t = e00;   // offset of row 0 at the producer's current time
+    int pleft = nsteps;   // steps not yet staged
+    auto issue = [&]() {
+      if (wl == 0) {
+        const int nact = min(ROWS, ng - pi0);
+        mbar_expect_tx(&full[slot_p], (uint32_t)(nact * ROW_BYTES));
+        unsigned char *dst = stages + slot_p * C::SLOT;
+        int64_t e = pe;
+        for (int rr = 0; rr < nact; ++rr, e += row_stride, dst += C::ROWB) {
+          if (HAS_D) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot_p]);
+          if (HAS_N || HAS_T) tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot_p]);
+          if (HAS_D || HAS_N) tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot_p]);
+        }
       }
+      slot_p = slot_p + 1 == ENG_STAGES ? 0 : slot_p + 1;
+      pi0 += ROWS;
+      pe += ROWS * row_stride;
+      if (pi0 >= ng) {
+        pi0 = 0;
+        pe_t += P.nchan;
+        pe = pe_t;
+      }
+      --pleft;
     };
 
     float sigc[8];
-    if (LEGS & LEG_NOISE) {
+    if (HAS_N) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
-        sigc[r] = (fabsf(c) <= 3.0e38f) ? c : 0.f;  // non-finite sigma -> 0 (ds.py:3575-3582)
+        const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
+        // non-finite sigma -> 0 (ds.py:3575-3582); taper * delta_f folded in
+        sigc[r] = (fabsf(c) <= 3.0e38f) ? c * (float)tapdf[r] : 0.f;
       }
     }
     cpx<T> S1[8];
@@ -286,29 +303,42 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       tA[r] = tAp[r] = tB[r] = tBp[r] = tC[r] = tCp[r] = (T)0;
     }
 
-    for (int k = 0; k < ENG_STAGES - 1 && k < nsteps; ++k) issue(k);
+    // ---- consumer state ------------------------------------------------------------
+    int ci0 = 0, ct = t0;                                   // first row / time of this step
+    int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
+    // Philox counter base of (row 0, time t0): row_id * N/2, row_id as in oracle/engine_ref.py
+    uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
+                       (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
+                      (uint64_t)(P.time_offset + t0));
+
+    for (int k = 0; k < ENG_STAGES - 1 && pleft > 0; ++k) issue();
     for (int step = 0; step < nsteps; ++step) {
       team_sync<WORKER>(bar_id);  // everyone is done with the slot about to be refilled
-      if (step + ENG_STAGES - 1 < nsteps) issue(step + ENG_STAGES - 1);
-      const uint32_t gs = gstep + (uint32_t)step, slot = gs % ENG_STAGES;
-      const int t = t0 + step / steps_per_t, i = (step % steps_per_t) * ROWS + sub;
+      if (pleft > 0) issue();
+      const int i = ci0 + sub;
       const bool active = i < ng;
-      const int bl = b0 + (active ? i : 0);
+      const int ia = active ? i : 0;
       float tint = 1.f;
-      if (LEGS & (LEG_NOISE | LEG_THERMAL)) tint = __ldg(P.int_time + (int64_t)bl * P.ntime + t);
-      mbar_wait(&full[slot], (gs / ENG_STAGES) & 1u);
-      const unsigned char *row = stages + slot * C::SLOT + sub * C::ROWB;
+      if (HAS_N || HAS_T) tint = __ldg(P.int_time + it_off + (int64_t)ia * P.ntime);
+      mbar_wait(&full[slot_c], par_c);
+      const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
       const float2 *vis_s = reinterpret_cast<const float2 *>(row);
       const float *ns_s = reinterpret_cast<const float *>(row + 8 * N);
       const unsigned char *fl_s = row + 12 * N;
 
-      if (LEGS & LEG_DATA) {
+      uint32_t keep = 0;  // bit r set: channel tau + TPR r of an active row is unflagged
+      if (HAS_D || HAS_N) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) keep |= (fl_s[tau + TPR * r] == 0 ? 1u : 0u) << r;
+        if (!active) keep = 0;
+      }
+
+      if (HAS_D) {
         cpx<T> v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const int n = tau + TPR * r;
-          const float2 c = active ? vis_s[n] : make_float2(0.f, 0.f);
-          const T m = (active && fl_s[n] == 0) ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
+          const float2 c = active ? vis_s[tau + TPR * r] : make_float2(0.f, 0.f);
+          const T m = (keep >> r) & 1u ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
           v[r] = {(T)c.x * m, (T)c.y * m};
         }
         TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
@@ -319,43 +349,39 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         }
       }
 
-      if (LEGS & LEG_NOISE) {
+      if (HAS_N) {
         cpx<float> v[8];
         if (P.noise_mode == 1) {
           // counter = row_id * N/2 + channel mod N/2 ; words (x,y) -> channel f < N/2,
           // (z,w) -> f + N/2: both belong to this thread (slots q and q + 4)
-          const uint64_t row_id =
-              ((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
-               (uint64_t)(P.bl_offset + bl)) * (uint64_t)P.ntime_total +
-              (uint64_t)(P.time_offset + t);
-          const float inv_t = tint;
+          const uint64_t ctr0 = (rid_t + (uint64_t)ia * (uint64_t)P.ntime_total) * (uint64_t)(N / 2) +
+                                (uint64_t)tau;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint64_t ctr = row_id * (uint64_t)(N / 2) + (uint64_t)(tau + TPR * q);
+            const uint64_t ctr = ctr0 + (uint64_t)(TPR * q);
             const u32x4 rn = philox4x32_10({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u},
                                            P.seed_lo, P.seed_hi);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int r = q + 4 * h, n = tau + TPR * r;
+              const int r = q + 4 * h;
               const uint32_t a = h ? rn.z : rn.x, b = h ? rn.w : rn.y;
               const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-              const float w = -0.69314718055994531f * __log2f(u1);      // -ln u1 >= 0
-              const float tn = inv_t * ns_s[n];
-              float amp = sigc[r] * fast_sqrt(w) * fast_rsqrt(tn);      // sigma * sqrt(-ln u1)
-              if (!(tn > 0.f) || !active || fl_s[n] != 0) amp = 0.f;    // invalid sigma / flagged
-              amp *= tapdf_f[r];
+              const float w = -0.69314718055994531f * __log2f(u1);  // -ln u1 >= 0
+              const float tn = tint * ns_s[tau + TPR * r];
+              // sigma * sqrt(-ln u1), with mask, taper and delta_f folded into sigc / keep
+              float amp = sigc[r] * fast_sqrt(w) * fast_rsqrt(tn);
+              if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
               float sn, cs;
               __sincosf(6.2831853071795865f * ((float)b * 2.3283064365386963e-10f), &sn, &cs);
               v[r] = {amp * cs, amp * sn};
             }
           }
         } else {  // injected freq-domain noise (parity mode): plain loads
-          const int64_t e = (((int64_t)p * P.nbl + bl) * P.ntime + t) * P.nchan + wstart;
+          const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const int n = tau + TPR * r;
-            const float2 c = active ? P.noise_in[e + n] : make_float2(0.f, 0.f);
-            const float m = (active && fl_s[n] == 0) ? tapdf_f[r] : 0.f;
+            const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
+            const float m = (keep >> r) & 1u ? (float)tapdf[r] : 0.f;
             v[r] = {c.x * m, c.y * m};
           }
         }
@@ -368,22 +394,41 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         }
       }
 
-      if (LEGS & LEG_THERMAL) {
+      if (HAS_T) {
+        // thermal sums use their own channel map: two runs of 4 consecutive channels
+        // per thread (c = 4 tau + 4 TPR h + j) -> two 128-bit loads + the right neighbours
         const T it = (tint > 0.f) ? (T)1 / (T)tint : (T)0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int n = tau + TPR * r;
-          const float n0 = ns_s[n], n1 = (n + 1 < N) ? ns_s[n + 1] : 0.f;
-          const bool e = active && n0 > 0.f && n1 > 0.f;  // both ends of panel n valid
-          const T a0 = e ? rsqrt_t<T>(n0) : (T)0, a1 = e ? rsqrt_t<T>(n1) : (T)0;
-          tA[r] += a0; tAp[r] += a1;
-          tB[r] += a0 * it; tBp[r] += a1 * it;
-          tC[r] += a0 * a0 * it; tCp[r] += a1 * a1 * it;
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = 4 * tau + 4 * TPR * h;
+          const float4 nv = *reinterpret_cast<const float4 *>(ns_s + c0);
+          const float nx = (c0 + 4 < N) ? ns_s[c0 + 4] : 0.f;  // no panel right of channel N-1
+          const float n5[5] = {nv.x, nv.y, nv.z, nv.w, nx};
+          T a5[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) a5[j] = (active && n5[j] > 0.f) ? rsqrt_t<T>(n5[j]) : (T)0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool e = a5[j] > (T)0 && a5[j + 1] > (T)0;  // both ends of the panel valid
+            const T a0 = e ? a5[j] : (T)0, a1 = e ? a5[j + 1] : (T)0;
+            const int q = 4 * h + j;
+            tA[q] += a0; tAp[q] += a1;
+            tB[q] += a0 * it; tBp[q] += a1 * it;
+            tC[q] += a0 * a0 * it; tCp[q] += a1 * a1 * it;
+          }
         }
       }
 
-      if ((step + 1) % steps_per_t == 0) {  // all rows of time t done
-        if (LEGS & LEG_DATA) {
+      // ---- advance the consumer; close the time when its last row is done -----------
+      slot_c = slot_c + 1 == ENG_STAGES ? 0 : slot_c + 1;
+      if (slot_c == 0) par_c ^= 1u;
+      ci0 += ROWS;
+      if (ci0 >= ng) {
+        ci0 = 0;
+        ++ct;
+        ++it_off;
+        ++rid_t;
+        if (HAS_D) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             cpx<T> sfull = S1[r];
@@ -396,7 +441,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
             S1[r] = {(T)0, (T)0};
           }
         }
-        if (LEGS & LEG_NOISE) {
+        if (HAS_N) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             cpx<float> sfull = Sn1[r];
@@ -409,12 +454,12 @@ engine_kernel(const __grid_constant__ EngineParams P) {
             Sn1[r] = {0.f, 0.f};
           }
         }
-        if (LEGS & LEG_THERMAL) {
+        if (HAS_T) {
           const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N;
           const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            T a = tA[r], ap = tAp[r], b = tB[r], bp = tBp[r];
+          for (int q = 0; q < 8; ++q) {
+            T a = tA[q], ap = tAp[q], b = tB[q], bp = tBp[q];
 #pragma unroll
             for (int off = TPR; off < 32; off <<= 1) {
               a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -422,22 +467,22 @@ engine_kernel(const __grid_constant__ EngineParams P) {
               b += __shfl_xor_sync(0xffffffffu, b, off);
               bp += __shfl_xor_sync(0xffffffffu, bp, off);
             }
-            const double l = __ldg(wlp + tau + TPR * r), rr = __ldg(wrp + tau + TPR * r);
+            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
+            const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
             if (sub == 0) th_all_acc += l * (double)a * (double)b + rr * (double)ap * (double)bp;
-            th_auto_acc += l * (double)tC[r] + rr * (double)tCp[r];
-            tA[r] = tAp[r] = tB[r] = tBp[r] = tC[r] = tCp[r] = (T)0;
+            th_auto_acc += l * (double)tC[q] + rr * (double)tCp[q];
+            tA[q] = tAp[q] = tB[q] = tBp[q] = tC[q] = tCp[q] = (T)0;
           }
         }
       }
     }
-    gstep += (uint32_t)nsteps;
 
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
     const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int kshift = (tau + TPR * r + N / 2) % N;
-      if (LEGS & LEG_DATA) {
+      if (HAS_D) {
         T s2 = S2[r];
 #pragma unroll
         for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
@@ -446,7 +491,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
           atomicAdd(P.pow_auto + 2 * (obase + kshift), (double)s2);
         }
       }
-      if (LEGS & LEG_NOISE) {
+      if (HAS_N) {
         float s2 = Sn2[r];
 #pragma unroll
         for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
@@ -456,7 +501,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         }
       }
     }
-    if (LEGS & LEG_THERMAL) {
+    if (HAS_T) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         th_all_acc += __shfl_xor_sync(0xffffffffu, th_all_acc, off);

@@ -7,8 +7,8 @@
 // (8, 8, ..., then N's remaining factor 2 or 4) and NB = 8 / R_p butterflies per
 // thread; butterfly m of thread tau is Stockham butterfly j = tau + TPR * m and
 // uses register slots { m + NB * q }.  Between passes values go through shared
-// memory (two ping-pong buffers, one team sync per pass), padded by one element
-// every eight to keep the strided writes conflict-free.
+// memory (two ping-pong buffers, one team sync per pass), XOR-swizzled to keep the
+// strided writes conflict-free.
 #pragma once
 #include "sds_common.cuh"
 
@@ -37,8 +37,10 @@ __host__ __device__ constexpr int fft_tw_offset(int N, int p) {
   return off;
 }
 __host__ __device__ constexpr int fft_tw_total(int N) { return fft_tw_offset(N, fft_npass(N)); }
-__host__ __device__ constexpr int fft_pad(int o) { return o + (o >> 3); }
-__host__ __device__ constexpr int fft_buf_elems(int N) { return N + (N >> 3); }
+// XOR swizzle of the exchange buffers: conflict-free for every write and read pattern
+// of the schedule below for N >= 128, cpx<float> and cpx<double> (scratch/pad_search.py)
+__host__ __device__ constexpr int fft_pad(int o) { return o ^ ((o >> 3) & 15); }
+__host__ __device__ constexpr int fft_buf_elems(int N) { return N; }
 
 __host__ __device__ constexpr int brev(int i, int bits) {
   int r = 0;
