@@ -306,7 +306,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
-    // Philox counter base of (row 0, time t0): row_id * N/2, row_id as in oracle/engine_ref.py
+    // Philox counter base of (row 0, time t0): row_id * N/2, row_id = ((s npol + p) nbl_total + b) ntime_total + t (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
                        (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
                       (uint64_t)(P.time_offset + t0));
