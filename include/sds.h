@@ -175,7 +175,8 @@ typedef struct sds_engine_desc {
  * trapezoid weights NOT folded in), freq fp64 [nspw][N];
  * noise_in c64 same shape as vis (noise_mode 2 only).
  * Outputs (fp64, accumulated INTO -- zero them first; sums over the batch's
- * times): pow_all/pow_auto/noise_all/noise_auto complex [ngroup][nspw][npol][N],
+ * times): pow_all/pow_auto/noise_all/noise_auto real [ngroup][nspw][npol][N] (with
+ * nuv == 1 the pair sums sum_ij x_i conj(x_j) = |sum_i x_i|^2 are real),
  * thermal_all/thermal_auto real [ngroup][nspw][npol] (already including the
  * 1/(npol sqrt2) and 1e-6 factors and the per-baseline 1/t_int).
  * workspace: sds_engine_workspace_bytes() bytes of device scratch. */

@@ -67,12 +67,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SDS_LIB", LIB_PATH)  # SDS_LIB: a development build of the same library
+    if not os.path.exists(path):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -m simpleds_b200.build` "
             "(nvcc, sm_100a).  simpleds_b200 has no CPU fallback."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args

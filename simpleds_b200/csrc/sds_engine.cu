@@ -19,94 +19,11 @@
 //            thermal partial sums from nsample.
 //   end of a time: P += |S1|^2 (the sum over ALL ordered pairs factorises),
 //   end of an item: fp64 atomics into the outputs (fftshift = index rotation).
-#include "sds_radix.cuh"
+#include "sds_engine.cuh"
 
 namespace sds {
 
-constexpr int ENG_STAGES = 3;
-#ifndef ENG_MINBLOCKS
-#define ENG_MINBLOCKS 1
-#endif
-constexpr int LEG_DATA = 1, LEG_NOISE = 2, LEG_THERMAL = 4;
-
-struct EngineParams {
-  const float2 *vis;
-  const uint8_t *flags;
-  const float *nsample;
-  const float *int_time;
-  const int32_t *goff;
-  const float *sigma_coef;
-  const float2 *noise_in;
-  const double *pol_factor;
-  const void *taper;      // T[N]
-  const void *tw;         // cpx<T>[fft_tw_total(N)]
-  const float *taper_f;   // float versions for the noise leg
-  const float2 *tw_f;
-  // workspace tables (engine_setup_kernel)
-  const int32_t *item_start;  // [ngroup + 1]
-  const double *wl, *wr;      // [nspw][npol][N] trapezoid-weighted thermal coefficients
-  int *counter;
-  double *pow_all, *pow_auto, *noise_all, *noise_auto, *th_all, *th_auto;
-  int64_t time_offset, ntime_total, bl_offset, nbl_total;
-  double delta_f;
-  uint32_t seed_lo, seed_hi;
-  int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
-  int win_start[SDS_MAX_WINDOWS];
-};
-
-// ---- PTX helpers (mbarrier + 1-D bulk TMA) -----------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
-                                            uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float y;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_rsqrt(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <typename T> __device__ __forceinline__ T rsqrt_t(float x);
-template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return fast_rsqrt(x); }
-template <> __device__ __forceinline__ double rsqrt_t<double>(float x) { return rsqrt((double)x); }
-
 // ---- setup: item table, thermal weights, counter -------------------------------
-// chunk(g) = clamp(target_rows / n_g, 1, ntime); items(g) = ceil(ntime / chunk) nspw npol
-__device__ __host__ __forceinline__ int eng_chunk(int ng, int ntime, int target_rows) {
-  int c = ng > 0 ? target_rows / ng : ntime;
-  return c < 1 ? 1 : (c > ntime ? ntime : c);
-}
-
 __global__ void engine_setup_kernel(const int32_t *__restrict__ goff, int ngroup, int ntime,
                                     int nspw, int npol, int N, int target_rows,
                                     const double *__restrict__ thermal_coef,
@@ -487,8 +404,8 @@ engine_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
         for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         if (sub == 0) {
-          atomicAdd(P.pow_all + 2 * (obase + kshift), (double)Pw[r]);
-          atomicAdd(P.pow_auto + 2 * (obase + kshift), (double)s2);
+          atomicAdd(P.pow_all + obase + kshift, (double)Pw[r]);
+          atomicAdd(P.pow_auto + obase + kshift, (double)s2);
         }
       }
       if (HAS_N) {
@@ -496,8 +413,8 @@ engine_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
         for (int off = TPR; off < 32; off <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         if (sub == 0) {
-          atomicAdd(P.noise_all + 2 * (obase + kshift), (double)Pn[r]);
-          atomicAdd(P.noise_auto + 2 * (obase + kshift), (double)s2);
+          atomicAdd(P.noise_all + obase + kshift, (double)Pn[r]);
+          atomicAdd(P.noise_auto + obase + kshift, (double)s2);
         }
       }
     }
@@ -545,6 +462,9 @@ static int launch_engine(const EngineParams &P, cudaStream_t st) {
   if (!configured) {
     SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    // several CTAs per SM only fit when the L1/shared split favours shared memory
+    SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   int dev = 0, nsm = 148, per_sm = 1;
@@ -562,25 +482,14 @@ static int launch_engine(const EngineParams &P, cudaStream_t st) {
   return SDS_OK;
 }
 
-// one launch for the leg mask `legs`; fp32 instantiates the fused masks, fp64
-// (register budget) one leg per launch
+// fp64 (register budget): one leg per launch
 template <typename T, int N>
 static int run_engine_n(EngineParams &P, int legs, cudaStream_t st) {
-  if constexpr (sizeof(T) == sizeof(float)) {
-    switch (legs) {
-      case 1: return launch_engine<T, N, 1>(P, st);
-      case 3: return launch_engine<T, N, 3>(P, st);
-      case 5: return launch_engine<T, N, 5>(P, st);
-      case 7: return launch_engine<T, N, 7>(P, st);
-      default: break;
-    }
-  } else {
-    switch (legs) {
-      case 1: return launch_engine<T, N, 1>(P, st);
-      case 2: return launch_engine<T, N, 2>(P, st);
-      case 4: return launch_engine<T, N, 4>(P, st);
-      default: break;
-    }
+  switch (legs) {
+    case 1: return launch_engine<T, N, 1>(P, st);
+    case 2: return launch_engine<T, N, 2>(P, st);
+    case 4: return launch_engine<T, N, 4>(P, st);
+    default: break;
   }
   set_error("sds_engine_run: leg mask %d is not instantiated", legs);
   return SDS_ENOTSUP;
@@ -688,7 +597,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   };
   if (pl.math == SDS_F32) {  // one pass over the inputs for every leg
     if ((rc = setup()) != SDS_OK) return rc;
-    return run_engine<float>(N, P, legs, st);
+    return run_engine_f32(N, P, legs, st, &g_last_launches);
   }
   for (int leg = 1; leg <= 4 && rc == SDS_OK; leg <<= 1)
     if (legs & leg) {

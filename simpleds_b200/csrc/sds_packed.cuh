@@ -1,0 +1,148 @@
+// Packed fp32x2 complex arithmetic for sm_100a and the packed version of the
+// 8-elements-per-thread Stockham schedule of sds_radix.cuh.
+//
+// Blackwell issues add/mul/fma on PAIRS of fp32 held in one 64-bit register
+// (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).  A complex sample
+// (re, im) is such a pair, so a complex add is ONE instruction and a complex
+// multiply TWO; lane swaps, per-lane negation and scalar broadcast are operand
+// modifiers of FADD2/FFMA2 (.LO_HI, .NP, .F32), so "multiply by -i" costs nothing.
+// The fused engine is bound by instruction issue, not by the FMA pipe, which is
+// what makes the packed forms pay.
+#pragma once
+#include "sds_radix.cuh"
+
+namespace sds {
+
+typedef unsigned long long f2;  // (lo, hi) = (re, im)
+
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(f2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 f2_scale(f2 a, float s) { return f2_mul(a, f2_make(s, s)); }
+// a * (-i) = (im, -re): folds into the .LO_HI.NP operand modifier of the consumer
+__device__ __forceinline__ f2 f2_mul_mi(f2 a) { return f2_make(f2_hi(a), -f2_lo(a)); }
+// complex product a * w
+__device__ __forceinline__ f2 f2_cmul(f2 a, f2 w) {
+  const float wx = f2_lo(w), wy = f2_hi(w);
+  return f2_fma(f2_make(-f2_hi(a), f2_lo(a)), f2_make(wy, wy), f2_mul(a, f2_make(wx, wx)));
+}
+// acc + (re^2, im^2): |a|^2 is the sum of the two lanes of the accumulator
+__device__ __forceinline__ f2 f2_norm_acc(f2 acc, f2 a) { return f2_fma(a, a, acc); }
+__device__ __forceinline__ float f2_hsum(f2 a) { return f2_lo(a) + f2_hi(a); }
+__device__ __forceinline__ f2 f2_shfl_xor(f2 v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+
+// In-place decimation-in-frequency butterflies (natural order in, bit-reversed out)
+template <int R> struct RadixP;
+template <> struct RadixP<1> {
+  static __device__ __forceinline__ void run(f2 *) {}
+};
+template <> struct RadixP<2> {
+  static __device__ __forceinline__ void run(f2 *a) {
+    const f2 t = a[0];
+    a[0] = f2_add(t, a[1]);
+    a[1] = f2_sub(t, a[1]);
+  }
+};
+template <> struct RadixP<4> {
+  static __device__ __forceinline__ void run(f2 *a) {
+    const f2 u0 = f2_add(a[0], a[2]), d0 = f2_sub(a[0], a[2]);
+    const f2 u1 = f2_add(a[1], a[3]), d1 = f2_mul_mi(f2_sub(a[1], a[3]));
+    a[0] = f2_add(u0, u1);
+    a[1] = f2_sub(u0, u1);
+    a[2] = f2_add(d0, d1);
+    a[3] = f2_sub(d0, d1);
+  }
+};
+template <> struct RadixP<8> {
+  static __device__ __forceinline__ void run(f2 *a) {
+    const float h = 0.70710678118654752440f;
+    f2 d[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      d[n] = f2_sub(a[n], a[n + 4]);
+      a[n] = f2_add(a[n], a[n + 4]);
+    }
+    a[4] = d[0];
+    a[5] = f2_scale(f2_add(d[1], f2_mul_mi(d[1])), h);   // * W8^1
+    a[6] = f2_mul_mi(d[2]);                              // * W8^2
+    a[7] = f2_scale(f2_sub(f2_mul_mi(d[3]), d[3]), h);   // * W8^3
+    RadixP<4>::run(a);
+    RadixP<4>::run(a + 4);
+  }
+};
+
+// Packed twin of TeamFft<float, N> (sds_radix.cuh): same thread/element ownership, same
+// twiddle table ([m][q-1][tau] of (re, im) pairs), same swizzled exchange buffers.
+template <int N> struct TeamFftP {
+  static constexpr int TPR = N / 8;
+  static constexpr int NPASS = fft_npass(N);
+  static constexpr int WORKER = TPR < 32 ? 32 : TPR;
+
+  template <int P>
+  static __device__ __forceinline__ void pass(f2 (&v)[8], f2 *bufA, f2 *bufB,
+                                              const f2 *__restrict__ tw, int tau, int bar) {
+    constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
+    if constexpr (P > 0) {
+      constexpr int OFF = fft_tw_offset(N, P);
+#pragma unroll
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+          v[m + NB * q] = f2_cmul(v[m + NB * q], tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tau]);
+    }
+    f2 *out = (P & 1) ? bufB : bufA;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      f2 a[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) a[q] = v[m + NB * q];
+      RadixP<R>::run(a);
+      if constexpr (P < NPASS - 1) {
+        const int j = tau + TPR * m;
+        const int base = (j / NS) * (NS * R) + (j % NS);
+#pragma unroll
+        for (int p = 0; p < R; ++p) out[fft_pad(base + p * NS)] = a[brev(p, LG)];
+      } else {
+#pragma unroll
+        for (int p = 0; p < R; ++p) v[m + NB * p] = a[brev(p, LG)];
+      }
+    }
+    if constexpr (P < NPASS - 1) {
+      team_sync<WORKER>(bar);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = out[fft_pad(tau + TPR * r)];
+      pass<P + 1>(v, bufA, bufB, tw, tau, bar);
+    }
+  }
+
+  static __device__ __forceinline__ void run(f2 (&v)[8], f2 *bufA, f2 *bufB,
+                                             const f2 *__restrict__ tw, int tau, int bar) {
+    pass<0>(v, bufA, bufB, tw, tau, bar);
+  }
+};
+
+}  // namespace sds

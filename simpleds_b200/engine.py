@@ -116,10 +116,11 @@ class RedundantPipeline:
 
     def reset(self):
         dev, shape = self.device, (self.ngroup, self.nspw, self.npol, self.nfreq)
-        self.pow_all = torch.zeros(shape, dtype=torch.complex128, device=dev)
-        self.pow_auto = torch.zeros(shape, dtype=torch.complex128, device=dev)
-        self.noise_all = torch.zeros(shape, dtype=torch.complex128, device=dev)
-        self.noise_auto = torch.zeros(shape, dtype=torch.complex128, device=dev)
+        # with one data set (Nuv = 1) the pair sums are real: sum_ij x_i conj(x_j) = |sum_i x_i|^2
+        self.pow_all = torch.zeros(shape, dtype=torch.float64, device=dev)
+        self.pow_auto = torch.zeros(shape, dtype=torch.float64, device=dev)
+        self.noise_all = torch.zeros(shape, dtype=torch.float64, device=dev)
+        self.noise_auto = torch.zeros(shape, dtype=torch.float64, device=dev)
         self.thermal_all = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
         self.thermal_auto = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
         self.ntimes_done = 0
@@ -172,9 +173,9 @@ class RedundantPipeline:
         rc = lib.sds_engine_run(
             self.plan.handle, C.byref(d), ptr(vis), ptr(fl), ptr(nsample), ptr(int_time),
             ptr(self.group_offset), ptr(self.sigma_coef32), ptr(self.thermal_coef if thermal else None),
-            ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all.view(torch.float64)),
-            ptr(self.pow_auto.view(torch.float64)), ptr(self.noise_all.view(torch.float64)),
-            ptr(self.noise_auto.view(torch.float64)), ptr(self.thermal_all), ptr(self.thermal_auto),
+            ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all),
+            ptr(self.pow_auto), ptr(self.noise_all), ptr(self.noise_auto), ptr(self.thermal_all),
+            ptr(self.thermal_auto),
             ptr(self._ws), stream_ptr(),
         )
         check(rc, "sds_engine_run")
@@ -187,8 +188,8 @@ class RedundantPipeline:
         S, N = self.nspw, self.nfreq
         x = ops.delay_transform(self.plan, vis, fl, self.delta_f, win_start=self.win_start)  # (S,P,B,T,N)
         s_all, s_auto = ops.cross_power_sums(x, group_offset=self.group_offset_host)
-        self.pow_all += s_all.sum(dim=3)
-        self.pow_auto += s_auto.sum(dim=3)
+        self.pow_all += s_all.sum(dim=3).real
+        self.pow_auto += s_auto.sum(dim=3).real
         self.kernel_launches += 2
         chans = np.asarray(self.win_start)[:, None] + np.arange(N)
         ns_w = ops.take_windows(nsample[None], chans)  # (S,P,B,T,N)
@@ -208,8 +209,8 @@ class RedundantPipeline:
                 self.kernel_launches += 1
             xn = ops.delay_transform(self.plan, nz, fl_w, self.delta_f)
             n_all, n_auto = ops.cross_power_sums(xn, group_offset=self.group_offset_host)
-            self.noise_all += n_all.sum(dim=3)
-            self.noise_auto += n_auto.sum(dim=3)
+            self.noise_all += n_all.sum(dim=3).real
+            self.noise_auto += n_auto.sum(dim=3).real
             self.kernel_launches += 3
         if thermal:
             t_all, t_auto = ops.thermal_power_sums(ns_w, ns_w, self.thermal_coef, self.freq_dev, it64,
