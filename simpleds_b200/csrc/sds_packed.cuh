@@ -143,6 +143,66 @@ template <int N> struct TeamFftP {
                                              const f2 *__restrict__ tw, int tau, int bar) {
     pass<0>(v, bufA, bufB, tw, tau, bar);
   }
+
+  // Two independent transforms in lockstep (one team sync per pass serves both): twice
+  // the instruction-level parallelism for the same number of barriers.  `a` uses
+  // bufA/bufB, `b` uses bufA + 2 * stride .. (the caller lays out 4 buffers per row).
+  template <int P>
+  static __device__ __forceinline__ void pass2(f2 (&a)[8], f2 (&b)[8], f2 *a0, f2 *a1, f2 *b0,
+                                               f2 *b1, const f2 *__restrict__ tw, int tau, int bar) {
+    constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
+    if constexpr (P > 0) {
+      constexpr int OFF = fft_tw_offset(N, P);
+#pragma unroll
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+          const f2 w = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tau];
+          a[m + NB * q] = f2_cmul(a[m + NB * q], w);
+          b[m + NB * q] = f2_cmul(b[m + NB * q], w);
+        }
+    }
+    f2 *oa = (P & 1) ? a1 : a0, *ob = (P & 1) ? b1 : b0;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      f2 x[R], y[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        x[q] = a[m + NB * q];
+        y[q] = b[m + NB * q];
+      }
+      RadixP<R>::run(x);
+      RadixP<R>::run(y);
+      if constexpr (P < NPASS - 1) {
+        const int j = tau + TPR * m;
+        const int base = (j / NS) * (NS * R) + (j % NS);
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          oa[fft_pad(base + p * NS)] = x[brev(p, LG)];
+          ob[fft_pad(base + p * NS)] = y[brev(p, LG)];
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          a[m + NB * p] = x[brev(p, LG)];
+          b[m + NB * p] = y[brev(p, LG)];
+        }
+      }
+    }
+    if constexpr (P < NPASS - 1) {
+      team_sync<WORKER>(bar);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        a[r] = oa[fft_pad(tau + TPR * r)];
+        b[r] = ob[fft_pad(tau + TPR * r)];
+      }
+      pass2<P + 1>(a, b, a0, a1, b0, b1, tw, tau, bar);
+    }
+  }
+  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], f2 *a0, f2 *a1, f2 *b0,
+                                              f2 *b1, const f2 *__restrict__ tw, int tau, int bar) {
+    pass2<0>(a, b, a0, a1, b0, b1, tw, tau, bar);
+  }
 };
 
 }  // namespace sds
