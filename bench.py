@@ -131,6 +131,21 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def measured_traffic(args, T):
+    """dram__bytes_read + dram__bytes_write of the fused kernel per launch from the committed
+    ncu capture of this configuration (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            for rec in json.load(f):
+                if (rec["config"], rec["precision"], rec["times"], rec["noise"], rec["thermal"]) == \
+                        (args.config, args.precision, T, not args.no_noise, not args.no_thermal):
+                    return rec["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def workload_config(args, cfg, pipe):
     c = dict(
         workload=f"{args.config}: synthetic {cfg['array']} redundant array, {cfg['nchan']} channels in "
@@ -147,9 +162,12 @@ def workload_config(args, cfg, pipe):
 
 # --------------------------------------------------------------------------- GPU arm
 class ClockSampler:
+    """nvidia-smi polled in the background; samples are attributed to the timed region by
+    line count (mark() before and after)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.proc = index, None
@@ -159,41 +177,60 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        t0 = time.time()
+        while self.mark() == 0 and time.time() - t0 < 5.0:  # first sample can take a second
+            time.sleep(0.05)
+
+    def _lines(self):
+        try:
+            with open(self.path) as f:
+                data = f.read()
+        except OSError:
+            return []
+        lines = data.split("\n")
+        return lines[:-1]  # the last element is an incomplete (or empty) line
+
+    def mark(self):
+        return len(self._lines())
 
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.proc is None:
-            return out
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def summary(self, lo, hi):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self._lines()[lo:hi]:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), samples=len(sm),
+                       power_w_max=float(np.max(power)))
+        out["reasons"] = sorted(reasons)
         try:
-            for ln in open(self.path):
-                f = [x.strip() for x in ln.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    smax.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
         return out
 
 
@@ -236,9 +273,8 @@ def run_gpu_arm(args, cfg):
                      noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
 
     def job_reduce():
-        if world > 1:
-            for t in pipe.sums().values():
-                dist.reduce(t.view(torch.float64) if t.is_complex() else t, dst=0, op=dist.ReduceOp.SUM)
+        # the path's single exchange step: one NCCL reduce of the flat fp64 partial sums
+        pipe.reduce(dst=0)
 
     for i in range(args.warmup):
         step(i)
@@ -253,6 +289,7 @@ def run_gpu_arm(args, cfg):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    mark0 = sampler.mark() if rank == 0 else 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
     for i in range(args.steps):
@@ -264,14 +301,33 @@ def run_gpu_arm(args, cfg):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    launches = pipe.kernel_launches - launches0  # kernels launched inside the timed region
+    clocks = None
+    if rank == 0:
+        mark1 = sampler.mark()
+        region = "timed region"
+        if mark1 - mark0 < 3 and sampler.proc is not None:
+            # a timed region shorter than a few nvidia-smi periods: keep the GPU on the same
+            # work (untimed) until three samples under load exist
+            keep = {k: v.clone() for k, v in pipe.sums().items()}
+            t_probe = time.time()
+            while sampler.mark() - mark0 < 3 and time.time() - t_probe < 3.0:
+                step(0)
+                torch.cuda.synchronize()
+            for k, v in pipe.sums().items():
+                v.copy_(keep[k])
+            pipe.ntimes_done = args.steps * T
+            mark1 = sampler.mark()
+            region = "timed region + identical untimed steps right after it (region shorter than 3 samples)"
+        sampler.stop()
+        clocks = sampler.summary(mark0, mark1)
+        clocks["sampled_over"] = region
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[1 + 2 * i].elapsed_time(ev[2 + 2 * i]) for i in range(args.steps)]
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         total_ms = float(tmax.item())
-    launches = pipe.kernel_launches - launches0
     pairs_per_step = pipe.pair_spectra(T)
     value = pairs_per_step * args.steps * world / (total_ms * 1e-3)
 
@@ -282,15 +338,47 @@ def run_gpu_arm(args, cfg):
     kern_ms = float(np.mean(step_ms))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=None, peak_source=peak_src, bytes_per_launch=alg_bytes,
-                    kernel_ms=kern_ms, kernel="sds::engine_kernel (+ engine_setup_kernel)")
+                    traffic=measured_traffic(args, T), peak_source=peak_src, bytes_per_launch=alg_bytes,
+                    kernel_ms=kern_ms, kernel="sds::engine_f32_kernel (+ engine_setup_kernel)"
+                    if args.precision == "complex64" else "sds::engine_kernel<double> x3 (+ setup)")
+
+    # per-leg breakdown of the fused kernel (explains the roofline fraction): same batch,
+    # noise and/or thermal legs switched off
+    if world == 1 and not args.no_breakdown and not (args.no_noise or args.no_thermal):
+        legs = {}
+        for name, kw in (("transform+pair_sums", dict(noise=None, thermal=False)),
+                         ("transform+pair_sums+thermal", dict(noise=None, thermal=True)),
+                         ("transform+pair_sums+noise", dict(noise="philox", thermal=False))):
+            for _ in range(3):
+                pipe.process(vis, flags, nsample, int_time, ntime_total=ntime_total, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                pipe.process(vis, flags, nsample, int_time, ntime_total=ntime_total, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            legs[name] = dict(kernel_ms=ms, achieved=alg_bytes / (ms * 1e-3) / 1e9,
+                              frac=alg_bytes / (ms * 1e-3) / 1e9 / peak)
+        roofline["legs"] = legs
+        pipe.reset()
+        for i in range(args.steps):  # restore the accumulators of the timed job for the sanity check
+            step(i)
+        torch.cuda.synchronize()
+
+    # end to end through the public API with pinned HOST buffers (H2D + D2H timed), every rank
+    e2e = None
+    if not args.no_e2e:
+        res_keep = {k: v.clone() for k, v in pipe.sums().items()}
+        e2e = run_e2e(args, cfg, pipe, red, freq, dev, world, rank)
+        for k, v in pipe.sums().items():
+            v.copy_(res_keep[k])
+        pipe.ntimes_done = args.steps * T
 
     line = None
     if rank == 0:
         res = pipe.result(ntimes=args.steps * T)
         finite = bool(torch.isfinite(res["power_all"].real).all().item())
-        # end to end through the public API with pinned HOST buffers (H2D + D2H timed)
-        e2e = run_e2e(args, cfg, pipe, red, freq, dev) if not args.no_e2e else None
         cpu = None
         if world == 1 and not args.no_cpu:
             r, dt = cpu_reference_rate(cfg, args.cpu_bl, args.cpu_times, 1)
@@ -314,16 +402,18 @@ def run_gpu_arm(args, cfg):
     return line
 
 
-def run_e2e(args, cfg, pipe, red, freq, dev):
+def run_e2e(args, cfg, pipe, red, freq, dev, world=1, rank=0):
     """Same metric through RedundantPipeline.process_host: pinned host arrays in, host
-    results out, every step."""
+    results out, every step; every rank runs its own batch, time = max over ranks."""
     import torch
+    import torch.distributed as dist
 
     from simpleds_b200 import synth
 
     Te = max(1, min(args.e2e_times, args.times))
     vis, flags, nsample, int_time = synth.make_visibilities(
-        red["group_offset"], cfg["npol"], Te, freq, seed=cfg["seed"] + 1, device=dev, t_int=cfg["t_int"])
+        red["group_offset"], cfg["npol"], Te, freq, seed=cfg["seed"] + 1, device=dev, t_int=cfg["t_int"],
+        time_offset=rank * Te)
     host = [t.cpu().pin_memory() for t in (vis, flags, nsample, int_time)]
     del vis, flags, nsample, int_time
     torch.cuda.empty_cache()
@@ -334,16 +424,24 @@ def run_e2e(args, cfg, pipe, red, freq, dev):
         pipe.reset()
         out = pipe.process_host(*host, noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         pipe.reset()
         out = pipe.process_host(*host, noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
     d2h = sum(v.nbytes for v in out.values() if hasattr(v, "nbytes"))
-    return dict(value=pipe.pair_spectra(Te) / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
-                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt, times_per_step=Te, steps=steps,
-                note="pinned host buffers -> H2D -> fused engine -> D2H of the per-group means")
+    return dict(value=world * pipe.pair_spectra(Te) / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt, times_per_step_per_gpu=Te, steps=steps,
+                h2d_gbs_per_gpu=(h2d + d2h) / dt / 1e9,
+                note="pinned host buffers -> chunked H2D on a copy stream overlapped with the fused "
+                     "engine -> D2H of the per-group means into pinned buffers; PCIe-bound")
 
 
 def main():
@@ -363,6 +461,7 @@ def main():
     ap.add_argument("--no-thermal", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = CONFIGS[args.config]

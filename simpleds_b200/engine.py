@@ -157,25 +157,31 @@ class RedundantPipeline:
             self._process_unfused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
         self.ntimes_done += T
 
-    def _process_fused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot):
+    def _process_fused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot,
+                       groups=None):
+        """One sds_engine_run.  ``groups`` = (g0, g1, goff_dev): the arrays hold only the
+        baselines of redundant groups g0..g1-1 (a chunk of process_host); the noise
+        counters stay keyed by the global baseline index."""
         lib = _lib.load()
         P, B, T, F0 = vis.shape
+        g0, g1, goff = (0, self.ngroup, self.group_offset) if groups is None else groups
         d = EngineDesc()
         d.npol, d.nbl, d.ntime, d.nchan = P, B, T, F0
-        d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, self.ngroup, 1, mode
+        d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, g1 - g0, 1, mode
         for i, w in enumerate(self.win_start):
             d.win_start[i] = w
-        d.time_offset, d.ntime_total, d.bl_offset, d.nbl_total = int(time_offset), ntot, 0, B
+        d.time_offset, d.ntime_total = int(time_offset), ntot
+        d.bl_offset, d.nbl_total = int(self.group_offset_host[g0]), self.nbl
         d.seed, d.delta_f = self.seed, self.delta_f
         need = lib.sds_engine_workspace_bytes(self.plan.handle, C.byref(d))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
         rc = lib.sds_engine_run(
             self.plan.handle, C.byref(d), ptr(vis), ptr(fl), ptr(nsample), ptr(int_time),
-            ptr(self.group_offset), ptr(self.sigma_coef32), ptr(self.thermal_coef if thermal else None),
-            ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all),
-            ptr(self.pow_auto), ptr(self.noise_all), ptr(self.noise_auto), ptr(self.thermal_all),
-            ptr(self.thermal_auto),
+            ptr(goff), ptr(self.sigma_coef32), ptr(self.thermal_coef if thermal else None),
+            ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all[g0:g1]),
+            ptr(self.pow_auto[g0:g1]), ptr(self.noise_all[g0:g1]), ptr(self.noise_auto[g0:g1]),
+            ptr(self.thermal_all[g0:g1]), ptr(self.thermal_auto[g0:g1]),
             ptr(self._ws), stream_ptr(),
         )
         check(rc, "sds_engine_run")
@@ -219,31 +225,108 @@ class RedundantPipeline:
             self.thermal_auto += t_auto.sum(dim=3)
             self.kernel_launches += 1
 
-    def process_host(self, vis, flags, nsample, int_time, **kw):
-        """``process`` for HOST arrays (numpy or CPU torch tensors, ideally pinned):
-        uploads them, runs the batch and returns ``result()`` as numpy arrays."""
-        dev = self.device
-        if not hasattr(self, "_stage"):
-            self._stage = {}
-        ins = []
+    def _host_chunks(self, ntime, chunk_bytes):
+        """Cut the group list into runs of whole groups of at most ~chunk_bytes of input."""
+        per_bl = 13 * self.npol * ntime * self.nchan
+        go, chunks, g0 = self.group_offset_host, [], 0
+        while g0 < self.ngroup:
+            g1 = g0 + 1
+            while g1 < self.ngroup and (go[g1 + 1] - go[g0]) * per_bl <= chunk_bytes:
+                g1 += 1
+            chunks.append((g0, g1))
+            g0 = g1
+        return chunks
+
+    def process_host(self, vis, flags, nsample, int_time, time_offset=0, ntime_total=None, noise="philox",
+                     thermal=True, chunk_bytes=1 << 29):
+        """``process`` for HOST arrays (numpy or CPU torch tensors; pinned memory makes the
+        copies asynchronous): the baselines are cut into chunks of whole redundant groups,
+        chunk k+1 is uploaded on a copy stream while chunk k runs, and ``result_host()``
+        is returned (pinned host buffers viewed as numpy arrays)."""
+        ins = {}
         for name, a, dt in (("vis", vis, torch.complex64), ("flags", flags, torch.uint8),
                             ("nsample", nsample, torch.float32), ("int_time", int_time, torch.float32)):
             t = torch.as_tensor(a)
             if t.dtype == torch.bool:
                 t = t.view(torch.uint8)
-            if t.dtype != dt:
-                raise ValueError(f"{name} must be {dt}")
-            buf = self._stage.get(name)
-            if buf is None or tuple(buf.shape) != tuple(t.shape):
-                buf = self._stage[name] = torch.empty(t.shape, dtype=dt, device=dev)
-            buf.copy_(t, non_blocking=True)
-            ins.append(buf)
-        self.process(*ins, **kw)
-        res = self.result()
+            if t.dtype != dt or t.device.type != "cpu":
+                raise ValueError(f"{name} must be a host array of {dt}")
+            ins[name] = t.contiguous()
+        P, B, T, F0 = ins["vis"].shape
+        if (P, B, F0) != (self.npol, self.nbl, self.nchan) or tuple(ins["int_time"].shape) != (B, T) \
+                or tuple(ins["flags"].shape) != (P, B, T, F0) or tuple(ins["nsample"].shape) != (P, B, T, F0):
+            raise ValueError("host arrays do not match the pipeline's (Npols, Nbls, T, Nchan)")
+        mode = {None: 0, "philox": 1}[noise]
+        ntot = T if ntime_total is None else int(ntime_total)
+        dev = self.device
+        if not self.fused:  # any window length: one upload, chained kernels
+            d = [ins[k].to(dev, non_blocking=True) for k in ("vis", "flags", "nsample", "int_time")]
+            self._process_unfused(*d, mode, None, thermal, time_offset, ntot)
+            self.ntimes_done += T
+            return self.result_host()
+
+        chunks = self._host_chunks(T, chunk_bytes)
+        go = self.group_offset_host
+        nb_max = max(int(go[g1] - go[g0]) for g0, g1 in chunks)
+        key = (nb_max, T)
+        if getattr(self, "_stage_key", None) != key:
+            n = P * nb_max * T * F0
+            self._stage = [dict(vis=torch.empty(n, dtype=torch.complex64, device=dev),
+                                flags=torch.empty(n, dtype=torch.uint8, device=dev),
+                                nsample=torch.empty(n, dtype=torch.float32, device=dev),
+                                int_time=torch.empty(nb_max * T, dtype=torch.float32, device=dev),
+                                ready=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
+            self._stage_key = key
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._goff_chunks = {}
+        cur = torch.cuda.current_stream(dev)
+        for st in self._stage:
+            st["done"].record(cur)  # the staging buffers are free once earlier work has drained
+        for k, (g0, g1) in enumerate(chunks):
+            st = self._stage[k % 2]
+            b0, b1 = int(go[g0]), int(go[g1])
+            nb = b1 - b0
+            if (g0, g1) not in self._goff_chunks:
+                self._goff_chunks[(g0, g1)] = torch.as_tensor((go[g0:g1 + 1] - b0).astype(np.int32), device=dev)
+            views = {name: st[name][:P * nb * T * F0].view(P, nb, T, F0) for name in ("vis", "flags", "nsample")}
+            itv = st["int_time"][:nb * T].view(nb, T)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(st["done"])
+                for name in ("vis", "flags", "nsample"):
+                    for p in range(P):  # one contiguous host block per polarisation
+                        views[name][p].copy_(ins[name][p, b0:b1], non_blocking=True)
+                itv.copy_(ins["int_time"][b0:b1], non_blocking=True)
+                st["ready"].record(self._copy_stream)
+            cur.wait_event(st["ready"])
+            self._process_fused(views["vis"], views["flags"], views["nsample"], itv, mode, None, thermal,
+                                time_offset, ntot, groups=(g0, g1, self._goff_chunks[(g0, g1)]))
+            st["done"].record(cur)
+        self.ntimes_done += T
+        return self.result_host()
+
+    def result_host(self, ntimes=None):
+        """``result()`` copied into (cached) pinned host buffers; numpy views are returned."""
+        res = self.result(ntimes)
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
         out = {}
         for k, v in res.items():
-            out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
-        return out
+            if not isinstance(v, torch.Tensor):
+                out[k] = v
+                continue
+            buf = self._pinned.get(k)
+            if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                buf = self._pinned[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            buf.copy_(v, non_blocking=True)
+            out[k] = buf
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+    def reduce(self, dst=0, all_ranks=False):
+        """Sum the ranks' partial accumulators (one collective; see shard.reduce_partials)."""
+        from . import shard
+
+        shard.reduce_partials(self.sums(), dst=dst, all_ranks=all_ranks)
 
     # ------------------------------------------------------------------ results
     def sums(self):
