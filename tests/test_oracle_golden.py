@@ -205,3 +205,20 @@ def test_thermal_masks_zero_nsample():
         pr["integration_time_s"], pr["nsample"],
     )
     assert np.all(sig0 == 0)
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors (Salmon et al. 2011): pins the counter-based generator that
+    the kernels' noise streams are compared against."""
+    from oracle.philox import philox4x32_10
+
+    u = np.uint32
+    kats = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kats:
+        got = philox4x32_10(*(np.array([c], dtype=u) for c in ctr), u(key[0]), u(key[1]))
+        assert [int(g[0]) for g in got] == want
