@@ -158,7 +158,7 @@ typedef struct sds_engine_desc {
   int32_t nspw;        /* spectral windows, each plan->nfreq channels           */
   int32_t ngroup;      /* redundant groups                                      */
   int32_t nuv;         /* 1: auto (one data set); 2: cross of two data sets     */
-  int32_t noise_mode;  /* 0 none, 1 Philox in-kernel, 2 injected (noise_in)     */
+  int32_t noise_mode;  /* 0 none, 1 in-kernel draw (below), 2 injected (noise_in) */
   int32_t win_start[SDS_MAX_WINDOWS];
   int64_t time_offset; /* global index of the batch's first time (RNG counter)  */
   int64_t ntime_total; /* global number of times             (RNG counter)      */
@@ -168,7 +168,14 @@ typedef struct sds_engine_desc {
   double delta_f;      /* Hz, scales the transform (utils.py:560)               */
 } sds_engine_desc;
 
-/* Inputs: vis  c64 [nuv][npol][nbl][ntime][nchan]; flags u8, nsample f32 same
+/* In-kernel noise (noise_mode 1), replacing utils.py:486-506 + ds.py:3544-3583: every
+ * sample gets sigma * sqrt(-ln u1) * exp(2 pi i u2) (Box-Muller), u1 and u2 24-bit uniforms
+ * cut from Philox4x32-7 words (Salmon et al. 2011) keyed by `seed`; the counter is the
+ * GLOBAL sample coordinate -- row_id * 3N/8 + 3 tau + k, row_id = ((s * npol + p) *
+ * nbl_total + bl_offset + b) * ntime_total + time_offset + t -- so the realisation does not
+ * depend on batching or sharding (exact word-to-channel map: oracle/engine_ref.py).
+ *
+ * Inputs: vis  c64 [nuv][npol][nbl][ntime][nchan]; flags u8, nsample f32 same
  * shape; int_time f32 [nbl][ntime]; group_offset int32[ngroup+1];
  * sigma_coef fp32 [nspw][npol][N] (as in sds_noise_sigma);
  * thermal_coef fp64 [nspw][npol][N] (as in sds_thermal_power_full, with the

@@ -12,7 +12,7 @@ import numpy as np
 from scipy.signal import windows
 
 from . import simpleds_oracle as orc
-from .philox import philox4x32_10
+from .philox import philox4x32
 
 _LO = np.uint64(0xFFFFFFFF)
 
@@ -66,32 +66,53 @@ def group_means(vis, flags, nsample, int_time, group_offset, freq_hz, spectral_w
     return out
 
 
+ENGINE_PHILOX_ROUNDS = 7
+
+
 def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
                       ntime_total=None, bl_offset=0, nbl_total=None):
     """The frequency-domain noise the fused kernel realises (before mask and taper):
-    sigma * sqrt(-ln u1) * exp(2 pi i u2), in float32 like the kernel.
+    sigma * sqrt(-ln u1) * exp(2 pi i u2), in float32 like the kernel (sds_engine_f32.cu).
 
     sigma_coef32 (S,P,N) float32; nsample (P,B,T,F0) float32; int_time (B,T) float32.
-    Counter = row_id * N/2 + (f mod N/2), row_id = ((s*P + p)*Bt + b)*Tt + t; the word
-    pair (x,y) serves channel f < N/2 and (z,w) channel f + N/2."""
+    A row (s,p,b,t) of N samples consumes 3N/8 Philox4x32-7 calls, counter =
+    row_id * 3N/8 + 3 tau + k (k = 0..2), row_id = ((s*P + p)*Bt + b)*Tt + t; thread tau
+    owns channels tau + (N/8) r, r = 0..7, and cuts its 12 words W into eight 48-bit draws
+    (24-bit radius uniform, 24-bit angle): for the pair (r = 2m, 2m + 1), base = 3m,
+      even: rad = W[base] >> 8,                           ang = (W[base] & 0xFF) << 16 | W[base+1] >> 16
+      odd : rad = (W[base+1] & 0xFFFF) << 8 | W[base+2] >> 24,   ang = W[base+2] & 0xFFFFFF."""
     P, B, T, _ = nsample.shape
     S, N = len(win_start), nfreq
+    tpr = N // 8
     Tt = T if ntime_total is None else ntime_total
     Bt = B if nbl_total is None else nbl_total
-    s_i, p_i, b_i, t_i, f_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
-                                          np.arange(N // 2), indexing="ij")
+    s_i, p_i, b_i, t_i, tau_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
+                                            np.arange(tpr), indexing="ij")
     row_id = ((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(Bt)
               + (b_i + bl_offset).astype(np.uint64)) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
-    ctr = row_id * np.uint64(N // 2) + f_i.astype(np.uint64)
-    r = philox4x32_10((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
-                      np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
-                      np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
-    a = np.concatenate([r[0], r[2]], axis=-1)  # channel f < N/2 then f + N/2
-    b = np.concatenate([r[1], r[3]], axis=-1)
+    words = []
+    for k in range(3):
+        ctr = row_id * np.uint64(3 * tpr) + np.uint64(3) * tau_i.astype(np.uint64) + np.uint64(k)
+        words += list(philox4x32((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
+                                 np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
+                                 np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
+                                 rounds=ENGINE_PHILOX_ROUNDS))
+    W = [w.astype(np.uint32) for w in words]  # 12 arrays (S,P,B,T,tpr)
+    rad24 = np.zeros((S, P, B, T, N), np.uint32)
+    ang24 = np.zeros((S, P, B, T, N), np.uint32)
+    u = np.uint32
+    for m in range(4):
+        w0, w1, w2 = W[3 * m], W[3 * m + 1], W[3 * m + 2]
+        ch_even = np.arange(tpr) + tpr * (2 * m)
+        ch_odd = np.arange(tpr) + tpr * (2 * m + 1)
+        rad24[..., ch_even] = w0 >> u(8)
+        ang24[..., ch_even] = ((w0 & u(0xFF)) << u(16)) | (w1 >> u(16))
+        rad24[..., ch_odd] = ((w1 & u(0xFFFF)) << u(8)) | (w2 >> u(24))
+        ang24[..., ch_odd] = w2 & u(0xFFFFFF)
     f32 = np.float32
-    u1 = (a.astype(f32) * f32(2.3283064365386963e-10) + f32(1.1641532182693481e-10)).astype(f32)
+    u1 = (rad24.astype(f32) * f32(2.0 ** -24) + f32(2.0 ** -25)).astype(f32)
     w = (-np.log(u1.astype(np.float64))).astype(f32)
-    ang = f32(6.2831853071795865) * (b.astype(f32) * f32(2.3283064365386963e-10))
+    ang = f32(6.2831853071795865) * (ang24.astype(f32) * f32(2.0 ** -24))
     chans = np.asarray(win_start)[:, None] + np.arange(N)
     ns_w = np.stack([nsample[..., chans[s]] for s in range(S)])  # (S,P,B,T,N)
     tn = int_time[None, None, :, :, None].astype(f32) * ns_w.astype(f32)

@@ -13,12 +13,14 @@ W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 _LO = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Philox4x32-R.  R = 10 is the Random123 / cuRAND default; R = 7 is the smallest
+    round count Salmon et al. report as Crush-resistant (used by the fused engine)."""
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3))
     k0 = np.asarray(k0, dtype=np.uint32)
     k1 = np.asarray(k1, dtype=np.uint32)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(rounds):
             p0 = M0 * c0.astype(np.uint64)
             p1 = M1 * c2.astype(np.uint64)
             n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c1 ^ k0
@@ -29,6 +31,10 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
             k0 = (k0 + W0).astype(np.uint32)
             k1 = (k1 + W1).astype(np.uint32)
     return c0, c1, c2, c3
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    return philox4x32(c0, c1, c2, c3, k0, k1, rounds=10)
 
 
 def normal_pairs(seed, n, offset=0):

@@ -269,29 +269,16 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       if (HAS_N) {
         cpx<float> v[8];
         if (P.noise_mode == 1) {
-          // counter = row_id * N/2 + channel mod N/2 ; words (x,y) -> channel f < N/2,
-          // (z,w) -> f + N/2: both belong to this thread (slots q and q + 4)
-          const uint64_t ctr0 = (rid_t + (uint64_t)ia * (uint64_t)P.ntime_total) * (uint64_t)(N / 2) +
-                                (uint64_t)tau;
+          float rad[8], cs[8], sn[8];
+          engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
+                            rad, cs, sn);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint64_t ctr = ctr0 + (uint64_t)(TPR * q);
-            const u32x4 rn = philox4x32_10({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u},
-                                           P.seed_lo, P.seed_hi);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = q + 4 * h;
-              const uint32_t a = h ? rn.z : rn.x, b = h ? rn.w : rn.y;
-              const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-              const float w = -0.69314718055994531f * __log2f(u1);  // -ln u1 >= 0
-              const float tn = tint * ns_s[tau + TPR * r];
-              // sigma * sqrt(-ln u1), with mask, taper and delta_f folded into sigc / keep
-              float amp = sigc[r] * fast_sqrt(w) * fast_rsqrt(tn);
-              if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
-              float sn, cs;
-              __sincosf(6.2831853071795865f * ((float)b * 2.3283064365386963e-10f), &sn, &cs);
-              v[r] = {amp * cs, amp * sn};
-            }
+          for (int r = 0; r < 8; ++r) {
+            const float tn = tint * ns_s[tau + TPR * r];
+            // sigma sqrt(-ln u1), with mask, taper and delta_f folded into sigc / keep
+            float amp = sigc[r] * rad[r] * fast_rsqrt(tn);
+            if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
+            v[r] = {amp * cs[r], amp * sn[r]};
           }
         } else {  // injected freq-domain noise (parity mode): plain loads
           const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;

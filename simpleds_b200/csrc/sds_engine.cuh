@@ -82,6 +82,56 @@ template <typename T> __device__ __forceinline__ T rsqrt_t(float x);
 template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return fast_rsqrt(x); }
 template <> __device__ __forceinline__ double rsqrt_t<double>(float x) { return rsqrt((double)x); }
 
+// ---- the fused engines' noise draw ------------------------------------------------
+#ifndef ENG_PHILOX_ROUNDS
+#define ENG_PHILOX_ROUNDS 7  // smallest Crush-resistant Philox4x32 (Salmon et al. 2011, table 2)
+#endif
+template <int ROUNDS>
+__device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+    u32x4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+    n.w = (uint32_t)p0;
+    c = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return c;
+}
+// Eight unit draws of the thread that owns channels tau + TPR r (r = 0..7) of row `row_id`:
+// rad = sqrt(-ln u1), (cs, sn) = exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox
+// calls, counter = row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight
+// 48-bit draws (24-bit radius uniform, 24-bit angle) -- IMAD.WIDE, 4 FMA-pipe cycles each on
+// B200, is the most expensive instruction of the kernel, so no generated bit is thrown away.
+template <int TPR>
+__device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, uint32_t k0, uint32_t k1,
+                                             float (&rad)[8], float (&cs)[8], float (&sn)[8]) {
+  const uint64_t ctr0 = row_id * (uint64_t)(3 * TPR) + (uint64_t)(3 * tau);
+  uint32_t W[12];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint64_t ctr = ctr0 + (uint64_t)k;
+    const u32x4 rn = philox4x32<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
+    W[4 * k] = rn.x; W[4 * k + 1] = rn.y; W[4 * k + 2] = rn.z; W[4 * k + 3] = rn.w;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int base = 3 * (r >> 1);
+    const uint32_t rad24 = (r & 1) ? (((W[base + 1] & 0xFFFFu) << 8) | (W[base + 2] >> 24))
+                                   : (W[base] >> 8);
+    const uint32_t ang24 = (r & 1) ? (W[base + 2] & 0xFFFFFFu)
+                                   : (((W[base] & 0xFFu) << 16) | (W[base + 1] >> 16));
+    const float u1 = fmaf((float)rad24, 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+    rad[r] = fast_sqrt(-0.69314718055994531f * __log2f(u1));  // sqrt(-ln u1)
+    __sincosf(6.2831853071795865f * ((float)ang24 * 5.9604644775390625e-8f), &sn[r], &cs[r]);
+  }
+}
+
 // chunk(g) = clamp(target_rows / n_g, 1, ntime); items(g) = ceil(ntime / chunk) nspw npol
 __device__ __host__ __forceinline__ int eng_chunk(int ng, int ntime, int target_rows) {
   int c = ng > 0 ? target_rows / ng : ntime;

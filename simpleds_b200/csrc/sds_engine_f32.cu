@@ -16,48 +16,29 @@ namespace sds {
 #ifndef E3_STAGES
 #define E3_STAGES 3
 #endif
-#ifndef E3_MINBLOCKS
-#define E3_MINBLOCKS 1
+#ifndef E3_WARPS_PER_SM
+#define E3_WARPS_PER_SM 12  // register budget: 65536 / (12 * 32) = 170 per thread
 #endif
-#ifndef E3_PHILOX_ROUNDS
-#define E3_PHILOX_ROUNDS 10
-#endif
-
-template <int ROUNDS>
-__device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
-    u32x4 n;
-    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
-    n.y = (uint32_t)p1;
-    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
-    n.w = (uint32_t)p0;
-    c = n;
-    k0 += W0;
-    k1 += W1;
-  }
-  return c;
-}
-
 template <int N> struct E3Cfg {
   static constexpr int TPR = N / 8;                     // threads per row
   static constexpr int TEAM = TPR < 32 ? 32 : TPR;      // threads per worker
   static constexpr int ROWS = TEAM / TPR;               // rows per step
   static constexpr int THREADS = TEAM < 128 ? 128 : TEAM;
   static constexpr int NWORKER = THREADS / TEAM;
+  // resident CTAs per SM the register allocation aims at (12 warps: measured best at N = 256)
+  static constexpr int MINB = (E3_WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (E3_WARPS_PER_SM * 32) / THREADS;
   static constexpr int ROWB = 13 * N;                   // vis 8N | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = N * 8;                     // one exchange buffer of one row
   static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
-  // per worker: 64 B barriers | E3_STAGES slots | ROWS * 4 exchange buffers | 2 N floats (P sums)
-  static constexpr int WORKER_BYTES = 64 + E3_STAGES * SLOT + ROWS * 4 * BUF + 8 * N;
+  // per worker: 64 B barriers | E3_STAGES slots | ROWS * 2 exchange buffers | 2 N floats (P sums)
+  //             | 6 floats per thread (thermal neighbour exchange at the close of a time)
+  static constexpr int WORKER_BYTES = 64 + E3_STAGES * SLOT + ROWS * 2 * BUF + 8 * N + 24 * TEAM;
   static constexpr int SMEM = TW_BYTES + NWORKER * WORKER_BYTES;
 };
 
 template <int N, int LEGS>
-__global__ void __launch_bounds__(E3Cfg<N>::THREADS, E3_MINBLOCKS)
+__global__ void __launch_bounds__(E3Cfg<N>::THREADS, E3Cfg<N>::MINB)
 engine_f32_kernel(const __grid_constant__ EngineParams P) {
   constexpr bool HAS_N = (LEGS & LEG_NOISE) != 0, HAS_T = (LEGS & LEG_THERMAL) != 0;
   using C = E3Cfg<N>;
@@ -72,10 +53,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   unsigned char *wbase = smem + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
-  f2 *bufA = reinterpret_cast<f2 *>(stages + E3_STAGES * C::SLOT + (size_t)(sub * 4) * C::BUF);
-  f2 *bufB = bufA + N, *bufC = bufA + 2 * N, *bufD = bufA + 3 * N;
+  f2 *bufA = reinterpret_cast<f2 *>(stages + E3_STAGES * C::SLOT + (size_t)(sub * 2) * C::BUF);
+  f2 *bufB = bufA + N;
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
-  float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT + (size_t)(ROWS * 4) * C::BUF);
+  float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT + (size_t)(ROWS * 2) * C::BUF);
+  float *nb_s = pw_s + 2 * N;  // [sub][run h][tau][3]: first-channel sums of each thermal run
   for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < E3_STAGES; ++i) mbar_init(&full[i], 1);
@@ -166,14 +148,22 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     }
     f2 S1[8], Sn1[8];                    // sum over the rows of a time: data and noise
     float S2[8], Sn2[8];                 // sum |x|^2
-    f2 tAA[8], tBB[8], tCC[8];           // thermal pair sums of the panel ends (left, right)
+    // thermal sums per channel, packed over adjacent channels (index 2 h + m: channels
+    // c0 + 2 m, c0 + 2 m + 1 of run h): A = sum a, B = sum a / t_int, C = sum a^2 / t_int with
+    // a = nsample^-1/2 (0 where invalid).  Rows with a valid sample next to an invalid one
+    // ("dirty" panels) additionally book what the panel mask removes into dfc[] (local memory,
+    // touched only on that rare path): per panel q, [0..2] left-end and [3..5] right-end deficits.
+    f2 tA[4], tB[4], tC[4];
+    float dfc[48];
+    bool dirty_time = false;
     double th_all_acc = 0.0, th_auto_acc = 0.0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       S1[r] = Sn1[r] = 0ull;
       S2[r] = Sn2[r] = 0.f;
-      tAA[r] = tBB[r] = tCC[r] = 0ull;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
 
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
@@ -213,29 +203,17 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_N) {
         if (P.noise_mode == 1) {
-          // counter = row_id * N/2 + channel mod N/2 ; words (x,y) -> channel f < N/2,
-          // (z,w) -> f + N/2: both belong to this thread (slots q and q + 4)
-          const uint64_t ctr0 = (rid_t + (uint64_t)ia * (uint64_t)P.ntime_total) * (uint64_t)(N / 2) +
-                                (uint64_t)tau;
+          float rad[8], cs[8], sn[8];
+          engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
+                            rad, cs, sn);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint64_t ctr = ctr0 + (uint64_t)(TPR * q);
-            const u32x4 rn = philox4x32<E3_PHILOX_ROUNDS>(
-                {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, P.seed_lo, P.seed_hi);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = q + 4 * h;
-              const uint32_t a = h ? rn.z : rn.x, b = h ? rn.w : rn.y;
-              const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-              const float tn = tint * ns_s[tau + TPR * r];
-              // sigma sqrt(-ln u1) = coef sqrt(-ln2 log2(u1)) / sqrt(t_int nsample); mask, taper
-              // and delta_f are folded into sigc / keep
-              float amp = sigc[r] * fast_sqrt(-0.69314718055994531f * __log2f(u1)) * fast_rsqrt(tn);
-              if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
-              float sn, cs;
-              __sincosf(6.2831853071795865f * ((float)b * 2.3283064365386963e-10f), &sn, &cs);
-              vn[r] = f2_scale(f2_make(cs, sn), amp);
-            }
+          for (int r = 0; r < 8; ++r) {
+            const float tn = tint * ns_s[tau + TPR * r];
+            // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample); mask, taper and
+            // delta_f are folded into sigc / keep
+            float amp = sigc[r] * rad[r] * fast_rsqrt(tn);
+            if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
+            vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
           }
         } else {  // injected freq-domain noise (parity mode): plain loads
           const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
@@ -247,7 +225,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
         }
         // both transforms in lockstep: two independent dependency chains per team sync
-        TeamFftP<N>::run2(vd, vn, bufA, bufB, bufC, bufD, tw_s, tau, bar_id);
+        TeamFftP<N>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           Sn1[r] = f2_add(Sn1[r], vn[r]);
@@ -263,31 +241,53 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
 
       if (HAS_T) {
-        // thermal sums use their own channel map: two runs of 4 consecutive channels
-        // per thread (c = 4 tau + 4 TPR h + j) -> two 128-bit loads + the right neighbours
+        // thermal sums use their own channel map: two runs of 4 consecutive channels per
+        // thread (c = 4 tau + 4 TPR h + j) -> two 128-bit loads + the right neighbours
         const float itv = (tint > 0.f) ? 1.f / tint : 0.f;
         const f2 it2 = f2_make(itv, itv);
+        bool dirty = false;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = 4 * tau + 4 * TPR * h;
           const float4 nv = *reinterpret_cast<const float4 *>(ns_s + c0);
-          const float nx = (c0 + 4 < N) ? ns_s[c0 + 4] : 0.f;  // no panel right of channel N-1
-          const float n5[5] = {nv.x, nv.y, nv.z, nv.w, nx};
-          float a5[5];
+          const float n4[4] = {nv.x, nv.y, nv.z, nv.w};
+          float a4[4];
           bool ok[5];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            ok[j] = active && n5[j] > 0.f;
-            a5[j] = ok[j] ? fast_rsqrt(n5[j]) : 0.f;
-          }
-#pragma unroll
           for (int j = 0; j < 4; ++j) {
-            // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697)
-            const f2 aa = f2_make(ok[j + 1] ? a5[j] : 0.f, ok[j] ? a5[j + 1] : 0.f);
-            const int q = 4 * h + j;
-            tAA[q] = f2_add(tAA[q], aa);
-            tBB[q] = f2_fma(aa, it2, tBB[q]);
-            tCC[q] = f2_fma(f2_mul(aa, aa), it2, tCC[q]);
+            ok[j] = active && n4[j] > 0.f;
+            a4[j] = ok[j] ? fast_rsqrt(n4[j]) : 0.f;
+          }
+          // right neighbour of the run (no panel right of channel N - 1)
+          ok[4] = (c0 + 4 < N) ? (active && ns_s[c0 + 4] > 0.f) : ok[3];
+          dirty |= (ok[0] != ok[1]) | (ok[1] != ok[2]) | (ok[2] != ok[3]) | (ok[3] != ok[4]);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const f2 aa = f2_make(a4[2 * m], a4[2 * m + 1]);
+            tA[2 * h + m] = f2_add(tA[2 * h + m], aa);
+            tB[2 * h + m] = f2_fma(aa, it2, tB[2 * h + m]);
+            tC[2 * h + m] = f2_fma(f2_mul(aa, aa), it2, tC[2 * h + m]);
+          }
+        }
+        if (dirty) {
+          // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697):
+          // book what the full sums above contain but the panel must not
+          if (!dirty_time) {
+#pragma unroll 1
+            for (int k = 0; k < 48; ++k) dfc[k] = 0.f;
+            dirty_time = true;
+          }
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
+            if (c + 1 >= N) continue;
+            const float nl = ns_s[c], nr = ns_s[c + 1];
+            if ((nl > 0.f) == (nr > 0.f)) continue;
+            const float av = fast_rsqrt(nl > 0.f ? nl : nr);
+            float *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
+            d[0] += av;
+            d[1] += av * itv;
+            d[2] += av * av * itv;
           }
         }
       }
@@ -319,22 +319,54 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         if (HAS_T) {
           const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N;
           const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N;
+          // the right end of a run's last panel is the first channel of the next thread's run
+          float *mine = nb_s + ((sub * 2) * TPR + tau) * 3;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            f2 ab = tAA[q], bb = tBB[q];
-#pragma unroll
-            for (int off = TPR; off < 32; off <<= 1) {
-              ab = f2_add(ab, f2_shfl_xor(ab, off));
-              bb = f2_add(bb, f2_shfl_xor(bb, off));
-            }
-            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
-            const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
-            if (sub == 0)
-              th_all_acc += l * (double)f2_lo(ab) * (double)f2_lo(bb) +
-                            rr * (double)f2_hi(ab) * (double)f2_hi(bb);
-            th_auto_acc += l * (double)f2_lo(tCC[q]) + rr * (double)f2_hi(tCC[q]);
-            tAA[q] = tBB[q] = tCC[q] = 0ull;
+          for (int h = 0; h < 2; ++h) {
+            mine[h * TPR * 3 + 0] = f2_lo(tA[2 * h]);
+            mine[h * TPR * 3 + 1] = f2_lo(tB[2 * h]);
+            mine[h * TPR * 3 + 2] = f2_lo(tC[2 * h]);
           }
+          team_sync<TEAM>(bar_id);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float nxt[3] = {0.f, 0.f, 0.f};
+            if (tau + 1 < TPR || h == 0) {
+              const float *src = (tau + 1 < TPR) ? mine + h * TPR * 3 + 3
+                                                 : nb_s + ((sub * 2 + 1) * TPR) * 3;
+              nxt[0] = src[0]; nxt[1] = src[1]; nxt[2] = src[2];
+            }
+            const float Ac[5] = {f2_lo(tA[2 * h]), f2_hi(tA[2 * h]), f2_lo(tA[2 * h + 1]),
+                                 f2_hi(tA[2 * h + 1]), nxt[0]};
+            const float Bc[5] = {f2_lo(tB[2 * h]), f2_hi(tB[2 * h]), f2_lo(tB[2 * h + 1]),
+                                 f2_hi(tB[2 * h + 1]), nxt[1]};
+            const float Cc[5] = {f2_lo(tC[2 * h]), f2_hi(tC[2 * h]), f2_lo(tC[2 * h + 1]),
+                                 f2_hi(tC[2 * h + 1]), nxt[2]};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = 4 * h + j;
+              float a = Ac[j], ap = Ac[j + 1], b = Bc[j], bp = Bc[j + 1], cc = Cc[j], cp = Cc[j + 1];
+              if (dirty_time) {
+                a -= dfc[6 * q + 0]; b -= dfc[6 * q + 1]; cc -= dfc[6 * q + 2];
+                ap -= dfc[6 * q + 3]; bp -= dfc[6 * q + 4]; cp -= dfc[6 * q + 5];
+              }
+              f2 ab = f2_make(a, ap), bb = f2_make(b, bp);
+#pragma unroll
+              for (int off = TPR; off < 32; off <<= 1) {
+                ab = f2_add(ab, f2_shfl_xor(ab, off));
+                bb = f2_add(bb, f2_shfl_xor(bb, off));
+              }
+              const int c = 4 * tau + 4 * TPR * h + j;
+              const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
+              if (sub == 0)
+                th_all_acc += l * (double)f2_lo(ab) * (double)f2_lo(bb) +
+                              rr * (double)f2_hi(ab) * (double)f2_hi(bb);
+              th_auto_acc += l * (double)cc + rr * (double)cp;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
+          dirty_time = false;
         }
       }
     }

@@ -145,11 +145,13 @@ template <int N> struct TeamFftP {
   }
 
   // Two independent transforms in lockstep (one team sync per pass serves both): twice
-  // the instruction-level parallelism for the same number of barriers.  `a` uses
-  // bufA/bufB, `b` uses bufA + 2 * stride .. (the caller lays out 4 buffers per row).
+  // the instruction-level parallelism for the same number of barriers.  Each transform
+  // has ONE exchange buffer (ba, bb); a second team sync after the reads of a pass makes
+  // the buffer reusable by the next pass (cheap for warp-sized teams, and it keeps the
+  // shared-memory footprint small enough for three CTAs per SM).
   template <int P>
-  static __device__ __forceinline__ void pass2(f2 (&a)[8], f2 (&b)[8], f2 *a0, f2 *a1, f2 *b0,
-                                               f2 *b1, const f2 *__restrict__ tw, int tau, int bar) {
+  static __device__ __forceinline__ void pass2(f2 (&a)[8], f2 (&b)[8], f2 *ba, f2 *bb,
+                                               const f2 *__restrict__ tw, int tau, int bar) {
     constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
     if constexpr (P > 0) {
       constexpr int OFF = fft_tw_offset(N, P);
@@ -162,7 +164,6 @@ template <int N> struct TeamFftP {
           b[m + NB * q] = f2_cmul(b[m + NB * q], w);
         }
     }
-    f2 *oa = (P & 1) ? a1 : a0, *ob = (P & 1) ? b1 : b0;
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
       f2 x[R], y[R];
@@ -178,8 +179,8 @@ template <int N> struct TeamFftP {
         const int base = (j / NS) * (NS * R) + (j % NS);
 #pragma unroll
         for (int p = 0; p < R; ++p) {
-          oa[fft_pad(base + p * NS)] = x[brev(p, LG)];
-          ob[fft_pad(base + p * NS)] = y[brev(p, LG)];
+          ba[fft_pad(base + p * NS)] = x[brev(p, LG)];
+          bb[fft_pad(base + p * NS)] = y[brev(p, LG)];
         }
       } else {
 #pragma unroll
@@ -193,15 +194,18 @@ template <int N> struct TeamFftP {
       team_sync<WORKER>(bar);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        a[r] = oa[fft_pad(tau + TPR * r)];
-        b[r] = ob[fft_pad(tau + TPR * r)];
+        a[r] = ba[fft_pad(tau + TPR * r)];
+        b[r] = bb[fft_pad(tau + TPR * r)];
       }
-      pass2<P + 1>(a, b, a0, a1, b0, b1, tw, tau, bar);
+      if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
+      pass2<P + 1>(a, b, ba, bb, tw, tau, bar);
     }
   }
-  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], f2 *a0, f2 *a1, f2 *b0,
-                                              f2 *b1, const f2 *__restrict__ tw, int tau, int bar) {
-    pass2<0>(a, b, a0, a1, b0, b1, tw, tau, bar);
+  // NOTE: the caller must team-sync between two run2 calls on the same buffers (the engine's
+  // step loop does, at the top of every step).
+  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], f2 *ba, f2 *bb,
+                                              const f2 *__restrict__ tw, int tau, int bar) {
+    pass2<0>(a, b, ba, bb, tw, tau, bar);
   }
 };
 
