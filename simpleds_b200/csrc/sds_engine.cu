@@ -19,6 +19,8 @@
 //            thermal partial sums from nsample.
 //   end of a time: P += |S1|^2 (the sum over ALL ordered pairs factorises),
 //   end of an item: fp64 atomics into the outputs (fftshift = index rotation).
+#include <stdlib.h>
+
 #include "sds_engine.cuh"
 
 namespace sds {
@@ -204,7 +206,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       for (int r = 0; r < 8; ++r) {
         const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
         // non-finite sigma -> 0 (ds.py:3575-3582); taper * delta_f folded in
-        sigc[r] = (fabsf(c) <= 3.0e38f) ? c * (float)tapdf[r] : 0.f;
+        sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * (float)tapdf[r] : 0.f;
       }
     }
     cpx<T> S1[8];
@@ -569,6 +571,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   P.npol = d->npol; P.nbl = d->nbl; P.ntime = d->ntime; P.nchan = d->nchan; P.nspw = d->nspw;
   P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
   P.target_rows = 64;
+  if (const char *tr = getenv("SDS_ENGINE_TARGET_ROWS")) P.target_rows = atoi(tr) > 0 ? atoi(tr) : 64;  // tuning knob
   for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
 
   const int legs = LEG_DATA | (d->noise_mode ? LEG_NOISE : 0) | (thermal ? LEG_THERMAL : 0);

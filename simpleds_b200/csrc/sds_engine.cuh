@@ -104,13 +104,15 @@ __device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 // Eight unit draws of the thread that owns channels tau + TPR r (r = 0..7) of row `row_id`:
-// rad = sqrt(-ln u1), (cs, sn) = exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox
-// calls, counter = row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight
-// 48-bit draws (24-bit radius uniform, 24-bit angle) -- IMAD.WIDE, 4 FMA-pipe cycles each on
-// B200, is the most expensive instruction of the kernel, so no generated bit is thrown away.
+// rad2 = sqrt(-log2 u1) (the caller folds sqrt(ln 2) into its amplitude), (cs, sn) =
+// exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox calls, counter =
+// row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight 48-bit draws (24-bit
+// radius uniform, 24-bit angle) -- IMAD.WIDE, 4 FMA-pipe cycles each on B200, is the most
+// expensive instruction of the kernel, so no generated bit is thrown away.
+constexpr float ENG_SQRT_LN2 = 0.83255461115769775635f;
 template <int TPR>
 __device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, uint32_t k0, uint32_t k1,
-                                             float (&rad)[8], float (&cs)[8], float (&sn)[8]) {
+                                             float (&rad2)[8], float (&cs)[8], float (&sn)[8]) {
   const uint64_t ctr0 = row_id * (uint64_t)(3 * TPR) + (uint64_t)(3 * tau);
   uint32_t W[12];
 #pragma unroll
@@ -122,13 +124,16 @@ __device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, uint32_t 
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int base = 3 * (r >> 1);
-    const uint32_t rad24 = (r & 1) ? (((W[base + 1] & 0xFFFFu) << 8) | (W[base + 2] >> 24))
+    // even draw: rad = W0[31:8], ang = W0[7:0] : W1[31:16]; odd: rad = W1[15:0] : W2[31:24],
+    // ang = W2[23:0]  (funnel shifts keep it at two instructions per field)
+    const uint32_t rad24 = (r & 1) ? (__funnelshift_l(W[base + 2], W[base + 1], 8) & 0xFFFFFFu)
                                    : (W[base] >> 8);
     const uint32_t ang24 = (r & 1) ? (W[base + 2] & 0xFFFFFFu)
-                                   : (((W[base] & 0xFFu) << 16) | (W[base + 1] >> 16));
+                                   : (__funnelshift_l(W[base + 1], W[base], 16) & 0xFFFFFFu);
     const float u1 = fmaf((float)rad24, 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-    rad[r] = fast_sqrt(-0.69314718055994531f * __log2f(u1));  // sqrt(-ln u1)
-    __sincosf(6.2831853071795865f * ((float)ang24 * 5.9604644775390625e-8f), &sn[r], &cs[r]);
+    rad2[r] = fast_sqrt(-__log2f(u1));
+    // angle = 2 pi ang24 / 2^24 in one multiply
+    __sincosf((float)ang24 * 3.7450702829239286e-7f, &sn[r], &cs[r]);
   }
 }
 

@@ -140,7 +140,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         if (P.noise_mode == 1) {
           const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
           // non-finite sigma -> 0 (ds.py:3575-3582); taper * delta_f folded in
-          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * tapdf[r] : 0.f;
+          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * tapdf[r] : 0.f;
         } else {
           sigc[r] = tapdf[r];
         }
@@ -191,39 +191,35 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 
       // ---- data leg: (1 - flag) * taper * delta_f ; noise leg: draw * sigma(nsample, t_int) --
       f2 vd[8], vn[8];
-      uint32_t keep = 0;  // bit r set: channel tau + TPR r of an active row is unflagged
+      // mask = (1 - flag) (ds.py:3503-3505); taper and delta_f ride on the same multiplier
+      // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
+      if (HAS_N && P.noise_mode == 1) {
+        float rad[8], cs[8], sn[8];
+        engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
+                          rad, cs, sn);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) keep |= (fl_s[tau + TPR * r] == 0 ? 1u : 0u) << r;
-      if (!active) keep = 0;
+        for (int r = 0; r < 8; ++r) {
+          const bool k = active && fl_s[tau + TPR * r] == 0;
+          vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581)
+          const float tn = tint * ns_s[tau + TPR * r];
+          const float amp = (k && tn > 0.f) ? sigc[r] * rad[r] * fast_rsqrt(tn) : 0.f;
+          vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
+        }
+      } else {
+        const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float m = (keep >> r) & 1u ? tapdf[r] : 0.f;  // ds.py:3503-3505, utils.py:552-560
-        const f2 c = active ? vis_s[tau + TPR * r] : 0ull;
-        vd[r] = f2_scale(c, m);
-      }
-      if (HAS_N) {
-        if (P.noise_mode == 1) {
-          float rad[8], cs[8], sn[8];
-          engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
-                            rad, cs, sn);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float tn = tint * ns_s[tau + TPR * r];
-            // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample); mask, taper and
-            // delta_f are folded into sigc / keep
-            float amp = sigc[r] * rad[r] * fast_rsqrt(tn);
-            if (!(tn > 0.f) || !((keep >> r) & 1u)) amp = 0.f;
-            vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
-          }
-        } else {  // injected freq-domain noise (parity mode): plain loads
-          const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float m = (keep >> r) & 1u ? sigc[r] : 0.f;
+        for (int r = 0; r < 8; ++r) {
+          const bool k = active && fl_s[tau + TPR * r] == 0;
+          vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          if (HAS_N) {  // injected freq-domain noise (parity mode): plain loads
             const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
+            const float m = k ? sigc[r] : 0.f;
             vn[r] = f2_make(c.x * m, c.y * m);
           }
         }
+      }
+      if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
         TeamFftP<N>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
 #pragma unroll
