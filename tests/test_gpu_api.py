@@ -61,7 +61,8 @@ def test_ft_kats_and_units(cuda_device, golden):
         utils.normalized_fourier_transform(np.zeros((4, 21, 3)), _q(2.5), axis=1)
 
 
-@pytest.mark.parametrize("n,f0", [(21, 21), (10, 21), (64, 203), (256, 1024), (203, 203)])
+@pytest.mark.parametrize("n,f0", [(21, 21), (10, 21), (64, 203), (256, 1024), (203, 203), (128, 512),
+                                  (512, 515), (1024, 1024), (2048, 2048)])
 def test_transform_flags_and_windows(cuda_device, n, f0):
     from simpleds_b200 import ops
     from simpleds_b200._lib import SDS_F32, SDS_F64
