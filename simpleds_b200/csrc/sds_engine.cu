@@ -83,7 +83,7 @@ __global__ void engine_setup_kernel(const int32_t *__restrict__ goff, int ngroup
 }
 
 // ---- the fused kernel ---------------------------------------------------------
-template <typename T, int N> struct EngCfg {
+template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr int TPR = N / 8;
   static constexpr int WORKER = TPR < 32 ? 32 : TPR;   // threads per worker
   static constexpr int ROWS = WORKER / TPR;            // rows per step
@@ -92,17 +92,23 @@ template <typename T, int N> struct EngCfg {
   static constexpr int ROWB = 13 * N;                  // vis 8N | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = fft_buf_elems(N) * (int)sizeof(cpx<T>);
-  static constexpr int TW_BYTES = fft_tw_total(N) * (int)sizeof(cpx<T>);
-  static constexpr int TWF_BYTES = fft_tw_total(N) * (int)sizeof(cpx<float>);
+  // twiddle tables only for the legs of this instantiation (the data leg's in T, the noise
+  // leg's in float): at N = 2048 in fp64 both tables, the ring and the exchange buffers
+  // would not fit the 227 KB of an SM
+  static constexpr bool SAME = sizeof(T) == sizeof(float);
+  static constexpr int TW_BYTES = (LEGS & LEG_DATA) ? fft_tw_total(N) * (int)sizeof(cpx<T>) : 0;
+  static constexpr int TWF_BYTES =
+      ((LEGS & LEG_NOISE) && !(SAME && (LEGS & LEG_DATA))) ? fft_tw_total(N) * (int)sizeof(cpx<float>) : 0;
+  static constexpr int TAB_BYTES = ((TW_BYTES + TWF_BYTES + 127) / 128) * 128;
   // per worker: barriers (64 B) | ENG_STAGES slots | 2 exchange buffers per row
   static constexpr int WORKER_BYTES = 64 + ENG_STAGES * SLOT + 2 * ROWS * BUF;
-  static constexpr int SMEM = ((TW_BYTES + TWF_BYTES + 127) / 128) * 128 + NWORKER * WORKER_BYTES;
+  static constexpr int SMEM = TAB_BYTES + NWORKER * WORKER_BYTES;
 };
 
 template <typename T, int N, int LEGS>
-__global__ void __launch_bounds__(EngCfg<T, N>::THREADS, ENG_MINBLOCKS)
+__global__ void __launch_bounds__(EngCfg<T, N, LEGS>::THREADS, ENG_MINBLOCKS)
 engine_kernel(const __grid_constant__ EngineParams P) {
-  using C = EngCfg<T, N>;
+  using C = EngCfg<T, N, LEGS>;
   constexpr int TPR = C::TPR, WORKER = C::WORKER, ROWS = C::ROWS;
   constexpr bool SAME = sizeof(T) == sizeof(float);
   constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
@@ -114,13 +120,12 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   cpx<float> *twf_s = SAME ? reinterpret_cast<cpx<float> *>(smem)
                            : reinterpret_cast<cpx<float> *>(smem + C::TW_BYTES);
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS) {
-    tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[i];
-    if (!SAME) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
+    if (C::TW_BYTES) tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[i];
+    if (C::TWF_BYTES) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
   }
   const int wid = threadIdx.x / WORKER, wl = threadIdx.x % WORKER;
   const int sub = wl / TPR, tau = wl % TPR, bar_id = 1 + wid;
-  unsigned char *wbase = smem + ((C::TW_BYTES + (SAME ? 0 : C::TWF_BYTES) + 127) / 128) * 128 +
-                         (size_t)wid * C::WORKER_BYTES;
+  unsigned char *wbase = smem + C::TAB_BYTES + (size_t)wid * C::WORKER_BYTES;
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
   cpx<T> *bufA = reinterpret_cast<cpx<T> *>(stages + ENG_STAGES * C::SLOT + (size_t)sub * 2 * C::BUF);
@@ -446,7 +451,7 @@ static thread_local int g_last_launches = 0;
 
 template <typename T, int N, int LEGS>
 static int launch_engine(const EngineParams &P, cudaStream_t st) {
-  using C = EngCfg<T, N>;
+  using C = EngCfg<T, N, LEGS>;
   static bool configured = false;
   if (!configured) {
     SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>,

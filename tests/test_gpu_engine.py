@@ -70,7 +70,7 @@ def check_against_oracle(res, ref, group_sizes, rtol, keys):
     "N,nwin,precision",
     [(64, 2, "complex64"), (128, 1, "complex64"), (256, 4, "complex64"), (512, 1, "complex64"),
      (1024, 1, "complex64"), (2048, 1, "complex64"),
-     (64, 1, "complex128"), (256, 2, "complex128"), (1024, 1, "complex128")],
+     (64, 1, "complex128"), (256, 2, "complex128"), (1024, 1, "complex128"), (2048, 1, "complex128")],
 )
 def test_fused_engine_matches_oracle_injected_noise(cuda_device, N, nwin, precision):
     group_sizes = [5, 1, 2, 9] if N <= 256 else [3, 1, 4]
