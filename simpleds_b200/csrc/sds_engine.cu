@@ -19,8 +19,6 @@
 //            thermal partial sums from nsample.
 //   end of a time: P += |S1|^2 (the sum over ALL ordered pairs factorises),
 //   end of an item: fp64 atomics into the outputs (fftshift = index rotation).
-#include <stdlib.h>
-
 #include "sds_engine.cuh"
 
 namespace sds {
@@ -576,7 +574,6 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   P.npol = d->npol; P.nbl = d->nbl; P.ntime = d->ntime; P.nchan = d->nchan; P.nspw = d->nspw;
   P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
   P.target_rows = 64;
-  if (const char *tr = getenv("SDS_ENGINE_TARGET_ROWS")) P.target_rows = atoi(tr) > 0 ? atoi(tr) : 64;  // tuning knob
   for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
 
   const int legs = LEG_DATA | (d->noise_mode ? LEG_NOISE : 0) | (thermal ? LEG_THERMAL : 0);

@@ -16,6 +16,9 @@ namespace sds {
 #ifndef E3_STAGES
 #define E3_STAGES 3
 #endif
+#ifndef E3_MIN_THREADS
+#define E3_MIN_THREADS 128
+#endif
 #ifndef E3_WARPS_PER_SM
 #define E3_WARPS_PER_SM 12  // register budget: 65536 / (12 * 32) = 170 per thread
 #endif
@@ -23,7 +26,7 @@ template <int N> struct E3Cfg {
   static constexpr int TPR = N / 8;                     // threads per row
   static constexpr int TEAM = TPR < 32 ? 32 : TPR;      // threads per worker
   static constexpr int ROWS = TEAM / TPR;               // rows per step
-  static constexpr int THREADS = TEAM < 128 ? 128 : TEAM;
+  static constexpr int THREADS = TEAM < E3_MIN_THREADS ? E3_MIN_THREADS : TEAM;
   static constexpr int NWORKER = THREADS / TEAM;
   // resident CTAs per SM the register allocation aims at (12 warps: measured best at N = 256)
   static constexpr int MINB = (E3_WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (E3_WARPS_PER_SM * 32) / THREADS;

@@ -38,7 +38,8 @@ __host__ __device__ constexpr int fft_tw_offset(int N, int p) {
 }
 __host__ __device__ constexpr int fft_tw_total(int N) { return fft_tw_offset(N, fft_npass(N)); }
 // XOR swizzle of the exchange buffers: conflict-free for every write and read pattern
-// of the schedule below for N >= 128, cpx<float> and cpx<double> (scratch/pad_search.py)
+// of the schedule below for N >= 128, cpx<float> and cpx<double> (exhaustive search over
+// shift/mask pairs, checked per 128-byte wavefront)
 __host__ __device__ constexpr int fft_pad(int o) { return o ^ ((o >> 3) & 15); }
 __host__ __device__ constexpr int fft_buf_elems(int N) { return N; }
 
