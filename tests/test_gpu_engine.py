@@ -174,3 +174,27 @@ def test_unfused_fallback_matches_oracle(cuda_device, wins, F0):
         check_against_oracle(res, ref, group_sizes, 1e-10 / 4, ["thermal_all", "thermal_noautos"])
     _, res = run_pipeline(a, wins, "complex64", "philox")
     assert np.all(np.isfinite(res["noise_power_all"])) and res["noise_power_all"].real.min() > 0
+
+
+def test_process_host_chunks_match_resident_path(cuda_device):
+    """RedundantPipeline.process_host (pinned host arrays, uploaded in chunks of whole groups
+    on a copy stream) == process() on device-resident arrays, noise realisation included
+    (its counters are keyed by the global baseline index, whatever the chunking)."""
+    group_sizes = [9, 1, 4, 30, 2, 6]
+    a = make_array(77, 2, group_sizes, 3, 256, zero_ns_frac=0.02)
+    wins = [(0, 127), (128, 255)]
+    _, whole = run_pipeline(a, wins, "complex64", "philox", seed=11)
+    from simpleds_b200.engine import RedundantPipeline
+
+    pipe = RedundantPipeline(a["freq"], wins, a["pols"], a["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                             precision="complex64", seed=11)
+    host = [torch.as_tensor(a[k]).pin_memory() for k in ("vis", "flags", "nsample", "int_time")]
+    per_bl = 13 * 2 * 3 * 256
+    assert len(pipe._host_chunks(3, 12 * per_bl)) >= 4  # several chunks, some holding several groups
+    got = pipe.process_host(*host, noise="philox", thermal=True, chunk_bytes=12 * per_bl)
+    for key in ("power_all", "power_noautos", "noise_power_all", "noise_power_noautos", "thermal_all",
+                "thermal_noautos"):
+        np.testing.assert_allclose(got[key], whole[key], rtol=1e-12, atol=0, equal_nan=True, err_msg=key)
+    # a second call accumulates (streaming) and reuses the staging buffers
+    got2 = pipe.process_host(*host, noise=None, thermal=False, chunk_bytes=12 * per_bl)
+    assert pipe.ntimes_done == 6 and np.all(np.isfinite(got2["power_all"]))
