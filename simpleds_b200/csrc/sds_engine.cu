@@ -143,6 +143,8 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   constexpr int ROW_BYTES = (HAS_D ? 8 * N : 0) + ((HAS_N || HAS_T) ? 4 * N : 0) +
                             ((HAS_D || HAS_N) ? N : 0);
   const int64_t row_stride = (int64_t)P.ntime * P.nchan;  // samples between baselines
+  // the team's first warp stages its rows (warp-uniform test: shfl from lane 0)
+  const bool issuer_warp = WORKER == 32 || __shfl_sync(0xffffffffu, wl, 0) == 0;
   uint32_t slot_c = 0, par_c = 0;  // consumer ring position / phase parity
   uint32_t slot_p = 0;             // producer ring position
   __shared__ int item_bcast[C::NWORKER];
@@ -181,7 +183,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     int64_t pe_t = e00;   // offset of row 0 at the producer's current time
     int pleft = nsteps;   // steps not yet staged
     auto issue = [&]() {
-      if (wl == 0) {
+      if (issuer_warp && elect_one()) {
         const int nact = min(ROWS, ng - pi0);
         mbar_expect_tx(&full[slot_p], (uint32_t)(nact * ROW_BYTES));
         unsigned char *dst = stages + slot_p * C::SLOT;

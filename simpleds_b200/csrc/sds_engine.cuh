@@ -68,6 +68,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows exactly one
+// thread runs the guarded code, so bulk-copy operands stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float fast_sqrt(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

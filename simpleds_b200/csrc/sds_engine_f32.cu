@@ -75,6 +75,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   const int total_items = P.item_start[P.ngroup];
   constexpr uint32_t ROW_BYTES = 13 * N;
   const int64_t row_stride = (int64_t)P.ntime * P.nchan;  // samples between baselines
+  // the team's first warp stages its rows (warp-uniform test: shfl from lane 0)
+  const bool issuer_warp = TEAM == 32 || __shfl_sync(0xffffffffu, tl, 0) == 0;
   uint32_t slot_c = 0, par_c = 0;  // consumer ring position / phase parity
   uint32_t slot_p = 0;             // producer ring position
   __shared__ int item_bcast[C::NWORKER];
@@ -89,7 +91,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       team_sync<TEAM>(bar_id);
       if (tl == 0) item_bcast[wid] = atomicAdd(P.counter, 1);
       team_sync<TEAM>(bar_id);
-      item = item_bcast[wid];
+      item = __shfl_sync(0xffffffffu, item_bcast[wid], 0);  // warp-uniform for the compiler too
     }
     if (item >= total_items) break;
     int lo = 0, hi = P.ngroup;  // largest g with item_start[g] <= item
@@ -114,7 +116,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     int64_t pe_t = e00;   // offset of row 0 at the producer's current time
     int pleft = nsteps;   // steps not yet staged
     auto issue = [&]() {
-      if (tl == 0) {
+      if (issuer_warp && elect_one()) {
         const int nact = min(ROWS, ng - pi0);
         mbar_expect_tx(&full[slot_p], (uint32_t)nact * ROW_BYTES);
         unsigned char *dst = stages + slot_p * C::SLOT;
