@@ -239,6 +239,9 @@ class DelaySpectrum:
                 raise UnitConversionError("trcvr must be in K")
             trcvr = trcvr.value
         trcvr = np.asarray(trcvr, dtype=np.float64)
+        if self.Nspws is None or self.Nfreqs is None:
+            # the reference fails inside UVParameter.expected_shape (t_ds.py:736-739)
+            raise ValueError("Missing shape parameter Nspws needed to calculate expected shape of parameter")
         if trcvr.size == 1:
             val = np.ones((self.Nspws, self.Nfreqs)) * float(trcvr.reshape(-1)[0])
         elif trcvr.ndim != 2 or trcvr.shape[0] != self.Nspws or trcvr.shape[1] != self.Nfreqs:

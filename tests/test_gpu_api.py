@@ -358,3 +358,25 @@ def test_uvdatalite_ingest_ordering(cuda_device):
                      np.full(len(a1), 42.95), 146.8e6 + 492610.84375 * np.arange(F), [1], uvw_array=uvw2)
     with pytest.raises(ValueError, match="single baseline vector"):
         DelaySpectrum(uv=uv2)
+
+
+def test_spectrum_on_no_data_and_twice(cuda_device):
+    """t_ds.py:742-745: no data -> ValueError; t_ds.py:1389-1436: calculate_delay_spectrum may be
+    called twice in a row (the second call finds delay-domain data and skips the transform,
+    ds.py:3617-3618) and gives the same power."""
+    from simpleds_b200 import DelaySpectrum
+
+    with pytest.raises(ValueError, match="No data has be loaded"):
+        DelaySpectrum().calculate_delay_spectrum()
+    with pytest.raises(ValueError):  # t_ds.py:736-739: trcvr alone cannot initialise
+        DelaySpectrum(trcvr=9.0)
+    pr = make_group(seed=6, P=2, B=4, T=3, F=21)
+    ds = _build_ds(pr)
+    ds.select_spectral_windows([(1, 3), (4, 6)])
+    ds.calculate_delay_spectrum()
+    first = ds.power_array.numpy().copy()
+    thermal = ds.thermal_power.numpy().copy()
+    ds.calculate_delay_spectrum()
+    assert ds.data_type == "delay"
+    assert np.array_equal(ds.power_array.numpy(), first)
+    assert np.array_equal(ds.thermal_power.numpy(), thermal)
