@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 #include "sds_radix.cuh"
@@ -92,6 +93,57 @@ extern "C" int sds_plan_create(sds_plan **plan, int nfreq, int math, const doubl
     PLAN_TRY(cudaMemcpy(p.team_tw_f, tf.data(), sizeof(sds::cpx<float>) * nt, cudaMemcpyHostToDevice));
     PLAN_TRY(cudaMemcpy(p.team_tw_d, td.data(), sizeof(sds::cpx<double>) * nt, cudaMemcpyHostToDevice));
   }
+  if (!p.is_pow2 && nfreq >= 8 && nfreq <= 1024) {
+    // Bluestein: X[k] = c[k] sum_n (x[n] c[n]) b[k - n], c[n] = exp(-i pi n^2 / N), b = conj(c)
+    int M = 64;
+    while (M < 2 * nfreq - 1) M <<= 1;
+    const long double pi = 3.141592653589793238462643383279502884L;
+    std::vector<sds::cpx<double>> chirp(nfreq), bhat(M);
+    std::vector<std::pair<long double, long double>> b(M, {0.0L, 0.0L}), wm(M);
+    for (int n = 0; n < nfreq; ++n) {
+      const long long q = ((long long)n * n) % (2LL * nfreq);  // n^2 mod 2N keeps the angle exact
+      const long double a = pi * (long double)q / (long double)nfreq;
+      chirp[n] = {(double)cosl(a), (double)-sinl(a)};
+      b[n] = {cosl(a), sinl(a)};
+      if (n) b[M - n] = b[n];
+    }
+    for (int k = 0; k < M; ++k) {
+      const long double a = -2.0L * pi * (long double)k / (long double)M;
+      wm[k] = {cosl(a), sinl(a)};
+    }
+    for (int k = 0; k < M; ++k) {  // plain O(M^2) transform in long double, once per plan
+      long double sr = 0.0L, si = 0.0L;
+      int idx = 0;
+      for (int m = 0; m < M; ++m) {
+        sr += b[m].first * wm[idx].first - b[m].second * wm[idx].second;
+        si += b[m].first * wm[idx].second + b[m].second * wm[idx].first;
+        idx += k;
+        if (idx >= M) idx -= M;
+      }
+      bhat[k] = {(double)sr, (double)si};
+    }
+    std::vector<sds::cpx<float>> chirpf(nfreq), bhatf(M);
+    for (int n = 0; n < nfreq; ++n) chirpf[n] = {(float)chirp[n].x, (float)chirp[n].y};
+    for (int k = 0; k < M; ++k) bhatf[k] = {(float)bhat[k].x, (float)bhat[k].y};
+    const int nt = sds::fft_tw_total(M);
+    std::vector<sds::cpx<float>> tf(nt);
+    std::vector<sds::cpx<double>> td(nt);
+    sds::fill_team_twiddles<float>(M, tf.data());
+    sds::fill_team_twiddles<double>(M, td.data());
+    PLAN_TRY(cudaMalloc(&p.blue_chirp_f, sizeof(sds::cpx<float>) * nfreq));
+    PLAN_TRY(cudaMalloc(&p.blue_chirp_d, sizeof(sds::cpx<double>) * nfreq));
+    PLAN_TRY(cudaMalloc(&p.blue_bhat_f, sizeof(sds::cpx<float>) * M));
+    PLAN_TRY(cudaMalloc(&p.blue_bhat_d, sizeof(sds::cpx<double>) * M));
+    PLAN_TRY(cudaMalloc(&p.blue_tw_f, sizeof(sds::cpx<float>) * nt));
+    PLAN_TRY(cudaMalloc(&p.blue_tw_d, sizeof(sds::cpx<double>) * nt));
+    PLAN_TRY(cudaMemcpy(p.blue_chirp_f, chirpf.data(), sizeof(sds::cpx<float>) * nfreq, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.blue_chirp_d, chirp.data(), sizeof(sds::cpx<double>) * nfreq, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.blue_bhat_f, bhatf.data(), sizeof(sds::cpx<float>) * M, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.blue_bhat_d, bhat.data(), sizeof(sds::cpx<double>) * M, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.blue_tw_f, tf.data(), sizeof(sds::cpx<float>) * nt, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p.blue_tw_d, td.data(), sizeof(sds::cpx<double>) * nt, cudaMemcpyHostToDevice));
+    p.blue_m = M;
+  }
 #undef PLAN_TRY
   *plan = pl;
   return SDS_OK;
@@ -105,6 +157,12 @@ extern "C" int sds_plan_destroy(sds_plan *plan) {
   cudaFree(plan->p.twiddle_f);
   cudaFree(plan->p.team_tw_f);
   cudaFree(plan->p.team_tw_d);
+  cudaFree(plan->p.blue_chirp_f);
+  cudaFree(plan->p.blue_chirp_d);
+  cudaFree(plan->p.blue_bhat_f);
+  cudaFree(plan->p.blue_bhat_d);
+  cudaFree(plan->p.blue_tw_f);
+  cudaFree(plan->p.blue_tw_d);
   free(plan);
   return SDS_OK;
 }

@@ -107,6 +107,15 @@ struct Plan {
   cpx<float> *team_tw_f;   // sds_radix.cuh tables (power-of-two lengths 64..4096)
   cpx<double> *team_tw_d;
   int is_pow2;
+  // Bluestein (chirp-z) tables for other lengths: the length-N transform as a circular
+  // convolution of power-of-two length blue_m >= 2N - 1 (sds_fft_bluestein.cu)
+  int blue_m;                 // 0: not available
+  cpx<float> *blue_chirp_f;   // [N]  exp(-i pi n^2 / N)
+  cpx<double> *blue_chirp_d;
+  cpx<float> *blue_bhat_f;    // [M]  FFT_M of the wrapped exp(+i pi m^2 / N), |m| < N
+  cpx<double> *blue_bhat_d;
+  cpx<float> *blue_tw_f;      // team twiddles of length M
+  cpx<double> *blue_tw_d;
 };
 
 }  // namespace sds

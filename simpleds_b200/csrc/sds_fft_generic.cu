@@ -1,7 +1,8 @@
 // K1/K4 any-length path: batched shared-memory Stockham transform with runtime
-// radices.  Correct for every 1 <= N <= SDS_MAX_NFREQ (21, 203, ... of the
-// reference's bundled files); power-of-two lengths are routed to the register
-// radix kernels in sds_fft_pow2.cu by sds_delay_transform below.
+// radices.  Correct for every 1 <= N <= SDS_MAX_NFREQ; it serves the inverse branch
+// (utils.py:561-564) and the lengths the fast paths do not take.  sds_delay_transform below
+// routes forward transforms of power-of-two lengths to sds_fft_pow2.cu and of other lengths
+// 8..1024 (21, 203, ... of the reference's bundled files) to sds_fft_bluestein.cu.
 //
 // Replaces utils.py:548-566 and the mask multiply of ds.py:3503-3517: flag mask,
 // taper, transform, fftshift (an index rotation on the store) and the delta_x
@@ -151,6 +152,12 @@ int launch_pow2(const Plan &pl, const void *in, int in_dtype, int64_t in_row_str
                 const int32_t *win_start, double delta_x, void *out, int out_dtype,
                 cudaStream_t st);
 
+// non-power-of-two lengths (sds_fft_bluestein.cu); SDS_ENOTSUP when the plan has no tables
+int launch_bluestein(const Plan &pl, const void *in, int in_dtype, int64_t in_row_stride,
+                     const uint8_t *flags, int64_t flag_row_stride, int64_t nrows, int nwin,
+                     const int32_t *win_start, double delta_x, void *out, int out_dtype,
+                     cudaStream_t st);
+
 }  // namespace sds
 
 extern "C" int sds_delay_transform(const sds_plan *plan, const void *in, int in_dtype,
@@ -179,6 +186,11 @@ extern "C" int sds_delay_transform(const sds_plan *plan, const void *in, int in_
   if (!inverse && pl.is_pow2) {
     int rc = sds::launch_pow2(pl, in, in_dtype, in_row_stride, flags, flag_row_stride, nrows,
                               nwin, win_start, delta_x, out, out_dtype, st);
+    if (rc != SDS_ENOTSUP) return rc;
+  }
+  if (!inverse && pl.blue_m) {
+    int rc = sds::launch_bluestein(pl, in, in_dtype, in_row_stride, flags, flag_row_stride, nrows,
+                                   nwin, win_start, delta_x, out, out_dtype, st);
     if (rc != SDS_ENOTSUP) return rc;
   }
   if (pl.math == SDS_F64)
