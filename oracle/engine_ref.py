@@ -120,3 +120,49 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
         amp = sigma_coef32[:, :, None, None, :].astype(f32) * np.sqrt(w) / np.sqrt(tn)
     amp = np.where(tn > 0, amp, f32(0)).astype(f32)
     return (amp * np.cos(ang.astype(np.float64)) + 1j * amp * np.sin(ang.astype(np.float64))).astype(np.complex64)
+
+
+def engine_noise_freq_chirpz(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
+                             ntime_total=None, bl_offset=0, nbl_total=None):
+    """The noise of the chirp-z engine (window lengths that are not powers of two,
+    sds_engine_blue.cu): convolution length M = smallest power of two >= max(64, 2N - 1), row
+    team of TPR = M / 8 threads; thread tau draws channels tau + TPR r (r < 4) from two
+    Philox4x32-7 calls, counter = row_id * 2 TPR + 2 tau + k: word 2r is the 32-bit radius
+    uniform, word 2r + 1 the angle."""
+    P, B, T, _ = nsample.shape
+    S, N = len(win_start), nfreq
+    M = 64
+    while M < 2 * N - 1:
+        M *= 2
+    tpr = M // 8
+    Tt = T if ntime_total is None else ntime_total
+    Bt = B if nbl_total is None else nbl_total
+    s_i, p_i, b_i, t_i, tau_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
+                                            np.arange(tpr), indexing="ij")
+    row_id = ((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(Bt)
+              + (b_i + bl_offset).astype(np.uint64)) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
+    W = []
+    for k in range(2):
+        ctr = row_id * np.uint64(2 * tpr) + np.uint64(2) * tau_i.astype(np.uint64) + np.uint64(k)
+        W += list(philox4x32((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
+                             np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
+                             np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
+                             rounds=ENGINE_PHILOX_ROUNDS))
+    rad = np.zeros((S, P, B, T, 4 * tpr), np.uint32)
+    ang = np.zeros((S, P, B, T, 4 * tpr), np.uint32)
+    for r in range(4):
+        ch = np.arange(tpr) + tpr * r
+        rad[..., ch] = W[2 * r]
+        ang[..., ch] = W[2 * r + 1]
+    rad, ang = rad[..., :N], ang[..., :N]
+    f32 = np.float32
+    u1 = (rad.astype(f32) * f32(2.0 ** -32) + f32(2.0 ** -33)).astype(f32)
+    w = (-np.log(u1.astype(np.float64))).astype(f32)
+    a = (ang.astype(f32) * f32(2 * np.pi / 2.0 ** 32)).astype(np.float64)
+    chans = np.asarray(win_start)[:, None] + np.arange(N)
+    ns_w = np.stack([nsample[..., chans[s]] for s in range(S)])
+    tn = int_time[None, None, :, :, None].astype(f32) * ns_w.astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = sigma_coef32[:, :, None, None, :].astype(f32) * np.sqrt(w) / np.sqrt(tn)
+    amp = np.where(tn > 0, amp, f32(0)).astype(f32)
+    return (amp * np.cos(a) + 1j * amp * np.sin(a)).astype(np.complex64)

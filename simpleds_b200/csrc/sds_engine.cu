@@ -540,10 +540,15 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     set_error("sds_engine_run: the fused path handles nuv == 1 only (got %d)", d->nuv);
     return SDS_ENOTSUP;
   }
-  if (!pl.is_pow2 || N < 64 || N > 2048 || !pl.team_tw_f) {
-    set_error("sds_engine_run: fused path needs a power-of-two nfreq in 64..2048, got %d", N);
+  const bool pow2_path = pl.is_pow2 && N >= 64 && N <= 2048 && pl.team_tw_f;
+  // other window lengths: chirp-z engine (complex64 only)
+  const bool blue_path = !pl.is_pow2 && pl.blue_m != 0 && pl.math == SDS_F32;
+  if (!pow2_path && !blue_path) {
+    set_error("sds_engine_run: fused path needs a power-of-two nfreq in 64..2048, or another "
+              "length in 8..1024 with complex64 arithmetic; got nfreq %d", N);
     return SDS_ENOTSUP;
   }
+  const int npad = blue_path ? (N + 15) & ~15 : N;  // channels one staged row piece covers
   // 1-D bulk copies need 16-byte aligned sources for every array (flags are 1 B/sample)
   if (d->nchan % 16 != 0 || ((uintptr_t)vis | (uintptr_t)flags | (uintptr_t)nsample) % 16 != 0) {
     set_error("sds_engine_run: fused path needs nchan %% 16 == 0 and 16-byte aligned inputs");
@@ -553,6 +558,11 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     SDS_CHECK_ARG(d->win_start[w] >= 0 && d->win_start[w] + N <= d->nchan,
                   "sds_engine_run: window %d [%d, %d) outside the %d channels", w, d->win_start[w],
                   d->win_start[w] + N, d->nchan);
+    if (d->win_start[w] + npad > d->nchan) {
+      set_error("sds_engine_run: fused path stages %d channels per window; window %d does not "
+                "leave that many before the end of the row", npad, w);
+      return SDS_ENOTSUP;
+    }
     if (d->win_start[w] % 16 != 0) {
       set_error("sds_engine_run: fused path needs window starts that are multiples of 16");
       return SDS_ENOTSUP;
@@ -577,6 +587,10 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
   P.target_rows = 64;
   for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
+  P.nfreq = N;
+  P.blue_chirp = (const float2 *)pl.blue_chirp_f;
+  P.blue_bhat = (const float2 *)pl.blue_bhat_f;
+  P.blue_tw = (const float2 *)pl.blue_tw_f;
 
   const int legs = LEG_DATA | (d->noise_mode ? LEG_NOISE : 0) | (thermal ? LEG_THERMAL : 0);
   int rc = SDS_OK;
@@ -591,6 +605,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   };
   if (pl.math == SDS_F32) {  // one pass over the inputs for every leg
     if ((rc = setup()) != SDS_OK) return rc;
+    if (blue_path) return run_engine_blue(pl.blue_m, P, legs, st, &g_last_launches);
     return run_engine_f32(N, P, legs, st, &g_last_launches);
   }
   for (int leg = 1; leg <= 4 && rc == SDS_OK; leg <<= 1)

@@ -34,6 +34,11 @@ struct EngineParams {
   uint32_t seed_lo, seed_hi;
   int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
   int win_start[SDS_MAX_WINDOWS];
+  // windows whose length is not a power of two (sds_engine_blue.cu): chirp-z tables of the plan
+  int nfreq;                  // window length N
+  const float2 *blue_chirp;   // [N]
+  const float2 *blue_bhat;    // [M]
+  const float2 *blue_tw;      // team twiddles of length M
 };
 
 // ---- PTX helpers (mbarrier + 1-D bulk TMA) -----------------------------------
@@ -158,5 +163,30 @@ __device__ __host__ __forceinline__ int eng_chunk(int ng, int ntime, int target_
 
 // fp32 engine (sds_engine_f32.cu); returns an sds_status / cudaError_t, counts its launches
 int run_engine_f32(int N, const EngineParams &P, int legs, cudaStream_t st, int *launches);
+// fp32 engine for window lengths that are not powers of two (sds_engine_blue.cu), M = the plan's
+// convolution length
+int run_engine_blue(int M, const EngineParams &P, int legs, cudaStream_t st, int *launches);
+
+// Four unit draws of the thread that owns channels tau + TPR r (r = 0..3) of row `row_id` in the
+// chirp-z engine (N <= 4 TPR): two Philox calls, counter = row_id * 2 TPR + 2 tau + k; draw r
+// takes word 2r for the radius (32-bit uniform) and word 2r + 1 for the angle.
+template <int TPR>
+__device__ __forceinline__ void engine_draw4(uint64_t row_id, int tau, uint32_t k0, uint32_t k1,
+                                             float (&rad2)[4], float (&cs)[4], float (&sn)[4]) {
+  const uint64_t ctr0 = row_id * (uint64_t)(2 * TPR) + (uint64_t)(2 * tau);
+  uint32_t W[8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint64_t ctr = ctr0 + (uint64_t)k;
+    const u32x4 rn = philox4x32<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
+    W[4 * k] = rn.x; W[4 * k + 1] = rn.y; W[4 * k + 2] = rn.z; W[4 * k + 3] = rn.w;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float u1 = fmaf((float)W[2 * r], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    rad2[r] = fast_sqrt(-__log2f(u1));
+    __sincosf((float)W[2 * r + 1] * 1.4629180792671596e-9f, &sn[r], &cs[r]);  // 2 pi / 2^32
+  }
+}
 
 }  // namespace sds

@@ -110,9 +110,16 @@ class RedundantPipeline:
         self.reset()
 
     def _fused_ok(self):
+        """Window lengths the one-pass engine takes: powers of two 64..2048, or any other
+        length 8..1024 in complex64 (chirp-z engine); rows and windows 16-sample aligned."""
         n = self.nfreq
-        return (n & (n - 1)) == 0 and 64 <= n <= 2048 and self.nchan % 16 == 0 and \
-            all(w % 16 == 0 for w in self.win_start)
+        if self.nchan % 16 != 0 or any(w % 16 != 0 for w in self.win_start):
+            return False
+        if (n & (n - 1)) == 0:
+            return 64 <= n <= 2048
+        npad = (n + 15) // 16 * 16
+        return 8 <= n <= 1024 and self.precision == "complex64" and \
+            all(w + npad <= self.nchan for w in self.win_start)
 
     def reset(self):
         dev, shape = self.device, (self.ngroup, self.nspw, self.npol, self.nfreq)
