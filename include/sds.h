@@ -144,6 +144,10 @@ int sds_cross_power_avg(const void *a1, const void *a2, int dtype, int S, int P,
                         double *out_all, double *out_auto, sds_stream stream);
 
 /* ------------------------------------------------------------------------
+ * (Window lengths: powers of two 64..2048 in either arithmetic; any other length 8..1024 with
+ * an SDS_F32 plan through the chirp-z engine.  Rows and window starts must be multiples of 16
+ * samples and a window must leave ceil16(nfreq) samples before the end of its row; otherwise
+ * SDS_ENOTSUP and the caller chains the kernels above.)
  * Fused engine: window select + flag mask + taper + delay transform + noise
  * realisation + its transform + pair sums + thermal sums in ONE pass over the
  * 13 B/sample inputs (ds.py:3196-3338, 3487-3517, 3544-3583, 3585-3707 and
