@@ -156,3 +156,43 @@ def test_bundled_files_through_delay_spectrum(cuda_device, name, wins, precision
     av = ds.calculate_averaged_delay_spectrum(remove_autos=True)
     want = orc.average_power(ref["power_array"], remove_autos=True, over_time=True)
     assert_close(av["power"].numpy(), want, 4 * rtol * B, what="averaged power")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,wins", [("uvh5_odd.npz", [(0, 20)]), ("uvh5_paper12.npz", [(0, 202)]),
+                                       ("uvh5_paper12.npz", [(96, 116), (112, 132)])])
+def test_bundled_files_through_fused_pipeline(cuda_device, name, wins):
+    """The same real data through RedundantPipeline (one redundant group): 21 and 203 channels are
+    not powers of two, so this is the fused chirp-z engine; the row pitch is padded to a multiple
+    of 16 channels at ingest (the framework owns the device layout)."""
+    import torch
+
+    from oracle import engine_ref
+    from simpleds_b200.engine import RedundantPipeline
+
+    ex = extract_loops(load(name))
+    vis, flags, ns = (ex[k][0, 0] for k in ("vis", "flags", "nsample"))  # (P,B,T,F)
+    P, B, T, F = vis.shape
+    Fp = (F + 15) // 16 * 16
+    pad = lambda a, v: np.concatenate([a, np.full(a.shape[:-1] + (Fp - F,), v, a.dtype)], axis=-1)  # noqa: E731
+    df = ex["freq_array_hz"][0, 1] - ex["freq_array_hz"][0, 0]
+    freq = ex["freq_array_hz"][0, 0] + df * np.arange(Fp)
+    a = dict(vis=pad(vis.astype(np.complex64), 0), flags=pad(flags, True), nsample=pad(ns.astype(np.float32), 0),
+             int_time=ex["integration_time_s"].astype(np.float32))
+    go = np.array([0, B])
+    pipe = RedundantPipeline(freq, wins, ex["polarization_array"], go, trcvr_k=144.0, beam_area_sr=0.76,
+                             precision="complex64", seed=21)
+    assert pipe.fused
+    pipe.process(*(torch.as_tensor(a[k], device=cuda_device) for k in ("vis", "flags", "nsample", "int_time")),
+                 noise="philox", thermal=True)
+    res = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in pipe.result().items()}
+    N = wins[0][1] - wins[0][0] + 1
+    nz = engine_ref.engine_noise_freq_chirpz(pipe.sigma_coef32.cpu().numpy(), a["nsample"], a["int_time"],
+                                             pipe.win_start, N, 21)
+    ref = engine_ref.group_means(a["vis"], a["flags"], a["nsample"], a["int_time"], go, freq, wins,
+                                 ex["polarization_array"], 144.0, 0.76, noise_freq=nz)
+    for key, tol in (("power_all", 4 * RTOL_C64), ("power_noautos", 4 * B * RTOL_C64),
+                     ("noise_power_all", 1e-4), ("noise_power_noautos", B * 1e-4)):
+        assert_close(res[key][0], ref[key][0], tol, what=key)
+    np.testing.assert_allclose(res["thermal_all"][0], ref["thermal_all"][0], rtol=4e-5)
+    np.testing.assert_allclose(res["thermal_noautos"][0], ref["thermal_noautos"][0], rtol=4e-5 * B)
