@@ -53,6 +53,8 @@ class Unit:
         return Quantity(1.0 / np.asarray(o, dtype=float), self)
 
     def __rtruediv__(self, o):
+        if isinstance(o, (int, float)):  # 1.0 / unit is a unit in astropy
+            return Unit(float(o) / self.scale, [-a for a in self.dims])
         return Quantity(np.asarray(o, dtype=float), Unit(1.0 / self.scale, [-a for a in self.dims]))
 
     def __pow__(self, p):
@@ -72,7 +74,7 @@ def _u(scale, **d):
 NAMED = {
     "": _u(1), "m": _u(1, m=1), "s": _u(1, s=1), "K": _u(1, K=1), "mK": _u(1e-3, K=1), "sr": _u(1, sr=1),
     "Hz": _u(1, s=-1), "MHz": _u(1e6, s=-1), "GHz": _u(1e9, s=-1), "Jy": _u(1e-26, kg=1, s=-2),
-    "J": _u(1, kg=1, m=2, s=-2),
+    "J": _u(1, kg=1, m=2, s=-2), "ns": _u(1e-9, s=1),
 }
 
 
@@ -233,6 +235,15 @@ def load_reference():
     g2 = dict(np=npx, units=units, utils=utils, integrate=integrate)
     exec(cut(f"{REF}/delay_spectrum.py", "calculate_noise_power", "DelaySpectrum"), g2)
     exec(cut(f"{REF}/delay_spectrum.py", "calculate_thermal_sensitivity", "DelaySpectrum"), g2)
+    import copy
+
+    uvutils = types.ModuleType("uvutils")
+    uvutils._get_iterable = lambda x: x if hasattr(x, "__iter__") else (x,)
+    g3 = dict(np=npx, units=units, copy=copy, uvutils=uvutils)
+    exec(cut(f"{REF}/delay_spectrum.py", "select_spectral_windows", "DelaySpectrum"), g3)
+    exec(cut(f"{REF}/delay_spectrum.py", "_take_spectral_windows_from_data_like_array", "DelaySpectrum"), g3)
+    utils.select_spectral_windows = g3["select_spectral_windows"]
+    utils.take_windows = g3["_take_spectral_windows_from_data_like_array"]
     return g2["calculate_noise_power"], g2["calculate_thermal_sensitivity"], utils
 
 
@@ -277,6 +288,30 @@ def main():
             want_unit = parse_unit("K^2 sr^2 Hz^6")
             assert tp.unit.same_dims(want_unit) and abs(tp.unit.scale / want_unit.scale - 1) < 1e-15
             g[f"{tag}_thermal_power"] = np.asarray(tp)
+    # select_spectral_windows + _take_spectral_windows_from_data_like_array (3196-3338): the
+    # window gather (integer index math, must be bit-exact) and the delay axis
+    for tag, (U, P, B, T, F, wins) in dict(
+            w1=(1, 2, 3, 2, 21, [(0, 9), (10, 19)]), w2=(2, 1, 2, 3, 21, [(0, 10), (10, 20)]),
+            w3=(1, 1, 2, 2, 203, [(95, 115)])).items():
+        o = fake_self(rng, 1, U, P, B, T, F, [-5, -6][:P])
+        o.data_array = rng.standard_normal((1, U, P, B, T, F)) + 1j * rng.standard_normal((1, U, P, B, T, F))
+        o.noise_array = rng.standard_normal((1, U, P, B, T, F)) + 1j * rng.standard_normal((1, U, P, B, T, F))
+        o.flag_array = rng.random((1, U, P, B, T, F)) < 0.2
+        o.beam_sq_area = Quantity(rng.random((1, P, F)), NAMED["sr"])
+        o.update_cosmology = lambda: None
+        o.check = lambda **k: True
+        o._take_spectral_windows_from_data_like_array = types.MethodType(utils.take_windows, o)
+        for k in ("data_array", "noise_array", "nsample_array", "flag_array"):
+            g[f"{tag}_in_{k}"] = np.asarray(getattr(o, k)).copy()
+        for k in ("freq_array", "trcvr", "beam_area", "beam_sq_area"):
+            g[f"{tag}_in_{k}"] = np.asarray(getattr(o, k)).copy()
+        g[f"{tag}_wins"] = np.asarray(wins)
+        utils.select_spectral_windows(o, spectral_windows=wins, inplace=True)
+        for k in ("data_array", "noise_array", "nsample_array", "flag_array", "freq_array", "trcvr",
+                  "beam_area", "beam_sq_area"):
+            g[f"{tag}_out_{k}"] = np.asarray(getattr(o, k))
+        g[f"{tag}_out_delay_ns"] = np.asarray(o.delay_array.to("ns"))
+        assert (o.Nspws, o.Nfreqs, o.Ndelays) == (len(wins), wins[0][1] - wins[0][0] + 1, o.Nfreqs)
     np.savez_compressed(OUT, **g)
     print(OUT, {k: v.shape for k, v in g.items()})
 

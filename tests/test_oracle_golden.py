@@ -247,3 +247,20 @@ def test_noise_power_and_thermal_match_the_reference_method_bodies():
         else:
             th = orc.calculate_thermal_sensitivity(*args, z[f"{tag}_pols"], _w.blackmanharris)
             np.testing.assert_allclose(th, z[f"{tag}_thermal_power"], rtol=1e-13, atol=0)
+
+
+def test_select_spectral_windows_matches_the_reference_method_body():
+    """ds_golden.npz w1..w3: the reference's own select_spectral_windows and
+    _take_spectral_windows_from_data_like_array (delay_spectrum.py:3196-3338) executed on seeded
+    arrays -- the gather is integer index work and must be reproduced bit for bit; the delay
+    axis to the last ulp."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ds_golden.npz"))
+    for tag in ("w1", "w2", "w3"):
+        state = {k: z[f"{tag}_in_{k}"] for k in ("data_array", "noise_array", "nsample_array", "flag_array",
+                                                  "freq_array", "trcvr", "beam_area", "beam_sq_area")}
+        out = orc.select_spectral_windows(state, [tuple(w) for w in z[f"{tag}_wins"]])
+        for k in state:
+            assert np.array_equal(out[k], z[f"{tag}_out_{k}"]), (tag, k)
+        np.testing.assert_allclose(out["delay_array_ns"], z[f"{tag}_out_delay_ns"], rtol=1e-15, atol=1e-12)
