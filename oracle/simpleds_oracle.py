@@ -30,8 +30,11 @@ Pinning status ("Oracle"):
     reproduces ``tests/golden/ds_golden.npz`` to 1e-13 (``tests/test_oracle_golden.py``),
     including the sigma -> 0 masking of non-finite values and the Nuv = 2 case.
   * ``select_spectral_windows`` / ``_take_spectral_windows_from_data_like_array`` /
-    ``delay_array`` (delay_spectrum.py:3196-3338) are pinned the same way (bit-exact gather),
-    and additionally by the reference tests' literal constants (delay values of ``test_delay_spectrum.py:1619`` /
+    ``delay_array`` (delay_spectrum.py:3196-3338) and the driver
+    ``DelaySpectrum.normalized_fourier_transform`` / ``delay_transform`` /
+    ``calculate_delay_spectrum`` (3487-3542, 3585-3635; Nuv = 1 and 2) are pinned the same way
+    (bit-exact gather, data, noise and power tensors), and additionally by the reference
+    tests' literal constants (delay values of ``test_delay_spectrum.py:1619`` /
     ``test_io.py:294``, shapes of ``test_delay_spectrum.py:889-955``) on the bundled files
     (``tests/test_uvh5_golden.py``).  Thermal parity on samples with ``nsample == 0`` is
     UNPINNED (how the mask of ``np.ma.masked_invalid`` survives the product with an astropy

@@ -31,7 +31,16 @@ BASE = ("m", "kg", "s", "K", "sr")
 
 
 class Unit:
-    __array_ufunc__ = None  # ndarray <op> Unit defers to the reflected methods below
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
+        """ndarray <op> Unit (also the in-place forms): attach / combine like astropy does."""
+        other = inputs[0] if inputs[1] is self else inputs[1]
+        if ufunc is np.left_shift and inputs[1] is self:
+            return other.to(self) if isinstance(other, Quantity) else Quantity(np.ma.getdata(other), self)
+        if ufunc is np.multiply:
+            return self * other
+        if ufunc in (np.divide, np.true_divide):
+            return other / self if inputs[1] is self else self / other
+        return NotImplemented
 
     def __init__(self, scale, dims):
         self.scale, self.dims = float(scale), tuple(dims)
@@ -95,7 +104,10 @@ class Quantity(np.ndarray):
     __array_priority__ = 1000
 
     def __new__(cls, value, unit):
-        obj = np.asarray(value, dtype=float).view(cls)
+        value = np.asarray(value)
+        if not np.iscomplexobj(value):
+            value = value.astype(float)
+        obj = value.view(cls)
         obj.unit = unit
         return obj
 
@@ -113,6 +125,10 @@ class Quantity(np.ndarray):
 
     def __lshift__(self, unit):
         return self.to(unit)
+
+    @property
+    def si(self):
+        return Quantity(np.asarray(self) * self.unit.scale, Unit(1.0, self.unit.dims))
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kw):
         assert method == "__call__", (ufunc, method)
@@ -196,6 +212,7 @@ def units_module():
     m.Unit = parse_unit
     m.Quantity = Quantity
     m.UnitBase = Unit
+    m.dimensionless_unscaled = NAMED[""]
     m.quantity_input = lambda *a, **k: (lambda fn: fn)
     return m
 
@@ -225,7 +242,7 @@ def load_reference():
     utils = types.ModuleType("utils")
     import copy
 
-    g = dict(np=npx, units=units, const=const, copy=copy)
+    g = dict(np=npx, units=units, const=const, copy=copy, windows=windows)
     exec(cut(f"{REF}/utils.py", "jy_to_mk"), g)
     exec(cut(f"{REF}/utils.py", "cross_multiply_array"), g)
     exec(cut(f"{REF}/utils.py", "combine_nsamples"), g)
@@ -242,6 +259,16 @@ def load_reference():
     g3 = dict(np=npx, units=units, copy=copy, uvutils=uvutils)
     exec(cut(f"{REF}/delay_spectrum.py", "select_spectral_windows", "DelaySpectrum"), g3)
     exec(cut(f"{REF}/delay_spectrum.py", "_take_spectral_windows_from_data_like_array", "DelaySpectrum"), g3)
+    import warnings
+
+    exec(cut(f"{REF}/utils.py", "normalized_fourier_transform"), g)  # needs `windows` default arg
+    utils.normalized_fourier_transform, utils.cross_multiply_array = g["normalized_fourier_transform"], g["cross_multiply_array"]
+    g4 = dict(np=npx, units=units, utils=utils, warnings=warnings)
+    for name in ("normalized_fourier_transform", "delay_transform", "calculate_delay_spectrum"):
+        exec(cut(f"{REF}/delay_spectrum.py", name, "DelaySpectrum"), g4)
+    utils.ds_methods = {k: g4[k] for k in ("normalized_fourier_transform", "delay_transform",
+                                           "calculate_delay_spectrum")}
+    utils.thermal = g2["calculate_thermal_sensitivity"]
     utils.select_spectral_windows = g3["select_spectral_windows"]
     utils.take_windows = g3["_take_spectral_windows_from_data_like_array"]
     return g2["calculate_noise_power"], g2["calculate_thermal_sensitivity"], utils
@@ -312,6 +339,29 @@ def main():
             g[f"{tag}_out_{k}"] = np.asarray(getattr(o, k))
         g[f"{tag}_out_delay_ns"] = np.asarray(o.delay_array.to("ns"))
         assert (o.Nspws, o.Nfreqs, o.Ndelays) == (len(wins), wins[0][1] - wins[0][0] + 1, o.Nfreqs)
+    # the driver: DelaySpectrum.normalized_fourier_transform / delay_transform /
+    # calculate_delay_spectrum (3487-3542, 3585-3635) calling the real utils functions
+    for tag, (U, P, B, T, F) in dict(d1=(1, 2, 4, 3, 21), d2=(2, 1, 3, 2, 16)).items():
+        o = fake_self(rng, 1, U, P, B, T, F, [-5, -6][:P])
+        shape = (1, U, P, B, T, F)
+        o.data_array = Quantity(rng.standard_normal(shape) + 1j * rng.standard_normal(shape), NAMED["Jy"])
+        o.noise_array = Quantity(rng.standard_normal(shape) + 1j * rng.standard_normal(shape), NAMED["Jy"])
+        o.flag_array = rng.random(shape) < 0.15
+        o.data_type = "frequency"
+        o.set_delay = lambda: setattr(o, "data_type", "delay")
+        o.set_frequency = lambda: setattr(o, "data_type", "frequency")
+        o.update_cosmology = lambda **k: None
+        for name, fn in utils.ds_methods.items():
+            setattr(o, name, types.MethodType(fn, o))
+        o.calculate_thermal_sensitivity = types.MethodType(utils.thermal, o)
+        for k in ("data_array", "noise_array", "flag_array", "nsample_array", "freq_array", "trcvr",
+                  "beam_area", "integration_time"):
+            g[f"{tag}_in_{k}"] = np.asarray(getattr(o, k)).copy()
+        g[f"{tag}_pols"] = o.polarization_array
+        o.calculate_delay_spectrum()
+        assert o.data_type == "delay"
+        for k in ("data_array", "noise_array", "power_array", "noise_power", "thermal_power"):
+            g[f"{tag}_out_{k}"] = np.asarray(getattr(o, k))
     np.savez_compressed(OUT, **g)
     print(OUT, {k: v.shape for k, v in g.items()})
 

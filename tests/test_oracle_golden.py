@@ -264,3 +264,24 @@ def test_select_spectral_windows_matches_the_reference_method_body():
         for k in state:
             assert np.array_equal(out[k], z[f"{tag}_out_{k}"]), (tag, k)
         np.testing.assert_allclose(out["delay_array_ns"], z[f"{tag}_out_delay_ns"], rtol=1e-15, atol=1e-12)
+
+
+def test_calculate_delay_spectrum_matches_the_reference_driver():
+    """ds_golden.npz d1 (Nuv = 1), d2 (Nuv = 2): the reference's DelaySpectrum.
+    normalized_fourier_transform / delay_transform / calculate_delay_spectrum bodies
+    (delay_spectrum.py:3487-3542, 3585-3635) driving its real utils functions.  The oracle's
+    driver must give the same delay-domain data and noise, power tensors and thermal estimate."""
+    import os
+
+    from scipy.signal import windows as _w
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ds_golden.npz"))
+    for tag in ("d1", "d2"):
+        i = {k: z[f"{tag}_in_{k}"] for k in ("data_array", "noise_array", "flag_array", "nsample_array",
+                                              "freq_array", "trcvr", "beam_area", "integration_time")}
+        res = orc.calculate_delay_spectrum(i["data_array"], i["noise_array"], i["flag_array"], i["nsample_array"],
+                                           i["freq_array"], i["trcvr"], i["beam_area"], i["integration_time"],
+                                           z[f"{tag}_pols"], _w.blackmanharris)
+        for k in ("data_array", "noise_array", "power_array", "noise_power"):
+            assert np.array_equal(res[k], z[f"{tag}_out_{k}"]), (tag, k)  # same numpy calls: bit for bit
+        np.testing.assert_allclose(res["thermal_power"], z[f"{tag}_out_thermal_power"], rtol=1e-13, atol=0)
