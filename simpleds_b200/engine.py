@@ -9,7 +9,9 @@ delay, the mean over baseline pairs and times of the data power, of the power of
 a matching noise realisation, and of the thermal estimate, i.e. what
 ``select_spectral_windows -> generate_noise -> calculate_delay_spectrum ->
 mean`` gives per group.  One call of ``sds_engine_run`` (include/sds.h) does the
-work for power-of-two windows; other lengths go through the unfused kernels.
+work: power-of-two windows (64..2048) in either precision, any other window
+length 8..1024 in complex64 (chirp-z engine); unaligned layouts and complex128 with
+other lengths chain the API-level kernels instead.
 """
 import ctypes as C
 
