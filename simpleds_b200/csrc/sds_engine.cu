@@ -476,12 +476,12 @@ static int launch_engine(const EngineParams &P, cudaStream_t st) {
   return SDS_OK;
 }
 
-// fp64 (register budget): one leg per launch
+// fp64 (register budget): one leg per launch; the noise leg (fp32 in every mode) is served
+// by sds_engine_f32.cu
 template <typename T, int N>
 static int run_engine_n(EngineParams &P, int legs, cudaStream_t st) {
   switch (legs) {
     case 1: return launch_engine<T, N, 1>(P, st);
-    case 2: return launch_engine<T, N, 2>(P, st);
     case 4: return launch_engine<T, N, 4>(P, st);
     default: break;
   }
@@ -608,10 +608,19 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     if (blue_path) return run_engine_blue(pl.blue_m, P, legs, st, &g_last_launches);
     return run_engine_f32(N, P, legs, st, &g_last_launches);
   }
+  // complex128: data and thermal legs in fp64, one launch each (register budget); the noise
+  // realisation is fp32 in both modes and takes the packed engine
   for (int leg = 1; leg <= 4 && rc == SDS_OK; leg <<= 1)
     if (legs & leg) {
       if ((rc = setup()) != SDS_OK) return rc;
-      rc = run_engine<double>(N, P, leg, st);
+      if (leg == LEG_NOISE) {
+        EngineParams Pn = P;
+        Pn.taper = pl.taper_f;
+        Pn.tw = pl.team_tw_f;
+        rc = run_engine_f32(N, Pn, LEG_NOISE, st, &g_last_launches);
+      } else {
+        rc = run_engine<double>(N, P, leg, st);
+      }
     }
   return rc;
 }

@@ -43,7 +43,10 @@ template <int N> struct E3Cfg {
 template <int N, int LEGS>
 __global__ void __launch_bounds__(E3Cfg<N>::THREADS, E3Cfg<N>::MINB)
 engine_f32_kernel(const __grid_constant__ EngineParams P) {
-  constexpr bool HAS_N = (LEGS & LEG_NOISE) != 0, HAS_T = (LEGS & LEG_THERMAL) != 0;
+  // LEGS without LEG_DATA (the noise leg alone) serves the complex128 mode, whose data and
+  // thermal legs run in fp64 (sds_engine.cu) while the noise realisation stays fp32
+  constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
+                 HAS_T = (LEGS & LEG_THERMAL) != 0;
   using C = E3Cfg<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -118,11 +121,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     auto issue = [&]() {
       if (issuer_warp && elect_one()) {
         const int nact = min(ROWS, ng - pi0);
-        mbar_expect_tx(&full[slot_p], (uint32_t)nact * ROW_BYTES);
+        mbar_expect_tx(&full[slot_p], (uint32_t)nact * (HAS_D ? ROW_BYTES : 5u * N));
         unsigned char *dst = stages + slot_p * C::SLOT;
         int64_t e = pe;
         for (int rr = 0; rr < nact; ++rr, e += row_stride, dst += C::ROWB) {
-          tma_load_1d(dst, P.vis + e, 8 * N, &full[slot_p]);
+          if (HAS_D) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot_p]);
           tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot_p]);
           tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot_p]);
         }
@@ -205,7 +208,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const bool k = active && fl_s[tau + TPR * r] == 0;
-          vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581)
           const float tn = tint * ns_s[tau + TPR * r];
           const float amp = (k && tn > 0.f) ? sigc[r] * rad[r] * fast_rsqrt(tn) : 0.f;
@@ -216,7 +219,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const bool k = active && fl_s[tau + TPR * r] == 0;
-          vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           if (HAS_N) {  // injected freq-domain noise (parity mode): plain loads
             const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
             const float m = k ? sigc[r] : 0.f;
@@ -226,7 +229,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        TeamFftP<N>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
+        if (HAS_D) TeamFftP<N>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
+        else TeamFftP<N>::run(vn, bufA, bufB, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           Sn1[r] = f2_add(Sn1[r], vn[r]);
@@ -235,10 +239,12 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       } else {
         TeamFftP<N>::run(vd, bufA, bufB, tw_s, tau, bar_id);
       }
+      if (HAS_D) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        S1[r] = f2_add(S1[r], vd[r]);
-        S2[r] = fmaf(f2_lo(vd[r]), f2_lo(vd[r]), fmaf(f2_hi(vd[r]), f2_hi(vd[r]), S2[r]));
+        for (int r = 0; r < 8; ++r) {
+          S1[r] = f2_add(S1[r], vd[r]);
+          S2[r] = fmaf(f2_lo(vd[r]), f2_lo(vd[r]), fmaf(f2_hi(vd[r]), f2_hi(vd[r]), S2[r]));
+        }
       }
 
       if (HAS_T) {
@@ -310,7 +316,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
             sd = f2_add(sd, f2_shfl_xor(sd, off));
             if (HAS_N) sn = f2_add(sn, f2_shfl_xor(sn, off));
           }
-          if (sub == 0) pw_s[tau + TPR * r] += f2_hsum(f2_mul(sd, sd));
+          if (HAS_D && sub == 0) pw_s[tau + TPR * r] += f2_hsum(f2_mul(sd, sd));
           S1[r] = 0ull;
           if (HAS_N) {
             if (sub == 0) pw_s[N + tau + TPR * r] += f2_hsum(f2_mul(sn, sn));
@@ -383,9 +389,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         if (HAS_N) sn2 += __shfl_xor_sync(0xffffffffu, sn2, off);
       }
       if (sub == 0) {
-        atomicAdd(P.pow_all + obase + kshift, (double)pw_s[tau + TPR * r]);
-        atomicAdd(P.pow_auto + obase + kshift, (double)s2);
-        pw_s[tau + TPR * r] = 0.f;
+        if (HAS_D) {
+          atomicAdd(P.pow_all + obase + kshift, (double)pw_s[tau + TPR * r]);
+          atomicAdd(P.pow_auto + obase + kshift, (double)s2);
+          pw_s[tau + TPR * r] = 0.f;
+        }
         if (HAS_N) {
           atomicAdd(P.noise_all + obase + kshift, (double)pw_s[N + tau + TPR * r]);
           atomicAdd(P.noise_auto + obase + kshift, (double)sn2);
@@ -440,6 +448,7 @@ template <int N>
 static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *launches) {
   switch (legs) {
     case 1: return launch_f32<N, 1>(P, st, launches);
+    case 2: return launch_f32<N, 2>(P, st, launches);
     case 3: return launch_f32<N, 3>(P, st, launches);
     case 5: return launch_f32<N, 5>(P, st, launches);
     case 7: return launch_f32<N, 7>(P, st, launches);
