@@ -77,10 +77,11 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
     sigma_coef32 (S,P,N) float32; nsample (P,B,T,F0) float32; int_time (B,T) float32.
     A row (s,p,b,t) of N samples consumes 3N/8 Philox4x32-7 calls, counter =
     row_id * 3N/8 + 3 tau + k (k = 0..2), row_id = ((s*P + p)*Bt + b)*Tt + t; thread tau
-    owns channels tau + (N/8) r, r = 0..7, and cuts its 12 words W into eight 48-bit draws
-    (24-bit radius uniform, 24-bit angle): for the pair (r = 2m, 2m + 1), base = 3m,
-      even: rad = W[base] >> 8,                           ang = (W[base] & 0xFF) << 16 | W[base+1] >> 16
-      odd : rad = (W[base+1] & 0xFFFF) << 8 | W[base+2] >> 24,   ang = W[base+2] & 0xFFFFFF."""
+    owns channels tau + (N/8) r, r = 0..7, and cuts its 12 words W into eight 46-bit draws
+    (23-bit radius field, 23-bit angle field): for the pair (r = 2m, 2m + 1), (w0, w1, w2) = W[3m..3m+2],
+      even: rad = w0[22:0],   ang = w1[22:0]
+      odd : rad = w2[22:0],   ang = w2[30:24] : w1[31:24] : w0[31:24]
+    Each field becomes the float f = 1 + field 2^-23 in [1, 2); u1 = 2 - f, angle = 2 pi f."""
     P, B, T, _ = nsample.shape
     S, N = len(win_start), nfreq
     tpr = N // 8
@@ -98,21 +99,21 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
                                  np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
                                  rounds=ENGINE_PHILOX_ROUNDS))
     W = [w.astype(np.uint32) for w in words]  # 12 arrays (S,P,B,T,tpr)
-    rad24 = np.zeros((S, P, B, T, N), np.uint32)
-    ang24 = np.zeros((S, P, B, T, N), np.uint32)
+    rad23 = np.zeros((S, P, B, T, N), np.uint32)
+    ang23 = np.zeros((S, P, B, T, N), np.uint32)
     u = np.uint32
     for m in range(4):
         w0, w1, w2 = W[3 * m], W[3 * m + 1], W[3 * m + 2]
         ch_even = np.arange(tpr) + tpr * (2 * m)
         ch_odd = np.arange(tpr) + tpr * (2 * m + 1)
-        rad24[..., ch_even] = w0 >> u(8)
-        ang24[..., ch_even] = ((w0 & u(0xFF)) << u(16)) | (w1 >> u(16))
-        rad24[..., ch_odd] = ((w1 & u(0xFFFF)) << u(8)) | (w2 >> u(24))
-        ang24[..., ch_odd] = w2 & u(0xFFFFFF)
+        rad23[..., ch_even] = w0 & u(0x7FFFFF)
+        ang23[..., ch_even] = w1 & u(0x7FFFFF)
+        rad23[..., ch_odd] = w2 & u(0x7FFFFF)
+        ang23[..., ch_odd] = (((w2 >> u(24)) & u(0x7F)) << u(16)) | ((w1 >> u(24)) << u(8)) | (w0 >> u(24))
     f32 = np.float32
-    u1 = (rad24.astype(f32) * f32(2.0 ** -24) + f32(2.0 ** -25)).astype(f32)
+    u1 = (f32(2.0) - (f32(1.0) + rad23.astype(f32) * f32(2.0 ** -23))).astype(f32)  # exact
     w = (-np.log(u1.astype(np.float64))).astype(f32)
-    ang = f32(6.2831853071795865) * (ang24.astype(f32) * f32(2.0 ** -24))
+    ang = ((f32(1.0) + ang23.astype(f32) * f32(2.0 ** -23)) * f32(6.2831853071795865)).astype(f32)
     chans = np.asarray(win_start)[:, None] + np.arange(N)
     ns_w = np.stack([nsample[..., chans[s]] for s in range(S)])  # (S,P,B,T,N)
     tn = int_time[None, None, :, :, None].astype(f32) * ns_w.astype(f32)

@@ -277,8 +277,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         cpx<float> v[8];
         if (P.noise_mode == 1) {
           float rad[8], cs[8], sn[8];
-          engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
-                            rad, cs, sn);
+          engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const float tn = tint * ns_s[tau + TPR * r];
@@ -583,6 +582,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   P.time_offset = d->time_offset; P.ntime_total = d->ntime_total > 0 ? d->ntime_total : d->ntime;
   P.bl_offset = d->bl_offset; P.nbl_total = d->nbl_total > 0 ? d->nbl_total : d->nbl;
   P.delta_f = d->delta_f; P.seed_lo = (uint32_t)d->seed; P.seed_hi = (uint32_t)(d->seed >> 32);
+  philox_fill_keys(P.seed_lo, P.seed_hi, P.pkey);
   P.npol = d->npol; P.nbl = d->nbl; P.ntime = d->ntime; P.nchan = d->nchan; P.nspw = d->nspw;
   P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
   P.target_rows = 64;

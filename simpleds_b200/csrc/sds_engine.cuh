@@ -32,6 +32,7 @@ struct EngineParams {
   int64_t time_offset, ntime_total, bl_offset, nbl_total;
   double delta_f;
   uint32_t seed_lo, seed_hi;
+  uint32_t pkey[16];          // Philox round keys: pkey[2 r] = seed_lo + r W0, pkey[2 r + 1] = seed_hi + r W1
   int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
   int win_start[SDS_MAX_WINDOWS];
   // windows whose length is not a power of two (sds_engine_blue.cu): chirp-z tables of the plan
@@ -121,37 +122,84 @@ __device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
   }
   return c;
 }
+// Philox4x32 with the round keys taken from the kernel parameters (constant bank operands:
+// no key-schedule arithmetic in the loop)
+template <int ROUNDS>
+__device__ __forceinline__ u32x4 philox4x32_keyed(u32x4 c, const uint32_t (&key)[16]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+    u32x4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ key[2 * r];
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ key[2 * r + 1];
+    n.w = (uint32_t)p0;
+    c = n;
+  }
+  return c;
+}
+__host__ __device__ __forceinline__ void philox_fill_keys(uint32_t seed_lo, uint32_t seed_hi,
+                                                          uint32_t (&key)[16]) {
+  for (int r = 0; r < 8; ++r) {
+    key[2 * r] = seed_lo + (uint32_t)r * 0x9E3779B9u;
+    key[2 * r + 1] = seed_hi + (uint32_t)r * 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sin(float x) {
+  float y;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_cos(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // Eight unit draws of the thread that owns channels tau + TPR r (r = 0..7) of row `row_id`:
 // rad2 = sqrt(-log2 u1) (the caller folds sqrt(ln 2) into its amplitude), (cs, sn) =
 // exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox calls, counter =
-// row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight 48-bit draws (24-bit
-// radius uniform, 24-bit angle) -- IMAD.WIDE, 4 FMA-pipe cycles each on B200, is the most
-// expensive instruction of the kernel, so no generated bit is thrown away.
+// row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight 46-bit draws (23-bit
+// radius uniform, 23-bit angle).  Each field is OR-ed under the exponent of 1.0f (one LOP3 builds
+// the float f in [1, 2), no integer conversion): u1 = 2 - f in (0, 1], angle = 2 pi f (mod 2 pi).
+// Per word triple (w0, w1, w2) = W[3m .. 3m+2], draws r = 2m (even) and 2m + 1 (odd):
+//   even: radius field w0[22:0],  angle field w1[22:0]
+//   odd : radius field w2[22:0],  angle field w2[30:24] : w1[31:24] : w0[31:24]   (two PRMT)
+// IMAD.WIDE, 4 FMA-pipe cycles on B200, is the most expensive instruction of the kernel, so a row
+// takes three Philox calls per thread and not four.
 constexpr float ENG_SQRT_LN2 = 0.83255461115769775635f;
+__device__ __forceinline__ float unit_float_23(uint32_t bits) {  // [1, 2) from the low 23 bits
+  return __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+}
 template <int TPR>
-__device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, uint32_t k0, uint32_t k1,
+__device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, const uint32_t (&key)[16],
                                              float (&rad2)[8], float (&cs)[8], float (&sn)[8]) {
   const uint64_t ctr0 = row_id * (uint64_t)(3 * TPR) + (uint64_t)(3 * tau);
   uint32_t W[12];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint64_t ctr = ctr0 + (uint64_t)k;
-    const u32x4 rn = philox4x32<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
+    const u32x4 rn = philox4x32_keyed<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, key);
     W[4 * k] = rn.x; W[4 * k + 1] = rn.y; W[4 * k + 2] = rn.z; W[4 * k + 3] = rn.w;
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int base = 3 * (r >> 1);
-    // even draw: rad = W0[31:8], ang = W0[7:0] : W1[31:16]; odd: rad = W1[15:0] : W2[31:24],
-    // ang = W2[23:0]  (funnel shifts keep it at two instructions per field)
-    const uint32_t rad24 = (r & 1) ? (__funnelshift_l(W[base + 2], W[base + 1], 8) & 0xFFFFFFu)
-                                   : (W[base] >> 8);
-    const uint32_t ang24 = (r & 1) ? (W[base + 2] & 0xFFFFFFu)
-                                   : (__funnelshift_l(W[base + 1], W[base], 16) & 0xFFFFFFu);
-    const float u1 = fmaf((float)rad24, 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-    rad2[r] = fast_sqrt(-__log2f(u1));
-    // angle = 2 pi ang24 / 2^24 in one multiply
-    __sincosf((float)ang24 * 3.7450702829239286e-7f, &sn[r], &cs[r]);
+  for (int m = 0; m < 4; ++m) {
+    const uint32_t w0 = W[3 * m], w1 = W[3 * m + 1], w2 = W[3 * m + 2];
+    const uint32_t hi = __byte_perm(__byte_perm(w0, w1, 0x0073), w2, 0x0710);
+    const float fr[2] = {unit_float_23(w0), unit_float_23(w2)};
+    const float fa[2] = {unit_float_23(w1), unit_float_23(hi)};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rad2[2 * m + h] = fast_sqrt(-fast_lg2(2.0f - fr[h]));
+      const float ang = fa[h] * 6.2831853071795865f;
+      cs[2 * m + h] = fast_cos(ang);
+      sn[2 * m + h] = fast_sin(ang);
+    }
   }
 }
 

@@ -33,12 +33,42 @@ template <int N> struct E3Cfg {
   static constexpr int ROWB = 13 * N;                   // vis 8N | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = N * 8;                     // one exchange buffer of one row
+  static constexpr int XREGION = NWORKER * ROWS * 2 * BUF;  // all exchange buffers, aligned to BUF
   static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
-  // per worker: 64 B barriers | E3_STAGES slots | ROWS * 2 exchange buffers | 2 N floats (P sums)
-  //             | 6 floats per thread (thermal neighbour exchange at the close of a time)
-  static constexpr int WORKER_BYTES = 64 + E3_STAGES * SLOT + ROWS * 2 * BUF + 8 * N + 24 * TEAM;
-  static constexpr int SMEM = TW_BYTES + NWORKER * WORKER_BYTES;
+  // per worker: 64 B barriers | E3_STAGES slots | 2 N floats (P sums)
+  static constexpr int WORKER_BYTES = 64 + E3_STAGES * SLOT + 8 * N;
+  // BUF bytes of slack in front: the exchange region is aligned to BUF at run time
+  static constexpr int SMEM = BUF + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
+
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// team-wide OR of a predicate (one vote for a warp-sized team, a reducing named barrier otherwise)
+template <int TEAM_THREADS>
+__device__ __forceinline__ bool team_any(bool pred, int barrier_id) {
+  if constexpr (TEAM_THREADS <= 32) {
+    return __any_sync(0xffffffffu, pred);
+  } else {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "barrier.red.or.pred q, %2, %3, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "r"(barrier_id), "n"(TEAM_THREADS)
+        : "memory");
+    return r != 0;
+  }
+}
 
 template <int N, int LEGS>
 __global__ void __launch_bounds__(E3Cfg<N>::THREADS, E3Cfg<N>::MINB)
@@ -48,22 +78,26 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
                  HAS_T = (LEGS & LEG_THERMAL) != 0;
   using C = E3Cfg<N>;
+  using FFT = TeamFftX<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // exchange region first, aligned to the size of one buffer (TeamFftX addressing)
+  const uint32_t s0 = smem_u32(smem_raw);
+  unsigned char *smem = smem_raw + (((s0 + C::BUF - 1u) & ~(uint32_t)(C::BUF - 1)) - s0);
 
-  f2 *tw_s = reinterpret_cast<f2 *>(smem);
+  f2 *tw_s = reinterpret_cast<f2 *>(smem + C::XREGION);
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
     tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;
-  unsigned char *wbase = smem + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
+  // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
+  const uint32_t xa = smem_u32(smem) + (uint32_t)((wid * ROWS + sub) * 2) * C::BUF;
+  const typename FFT::Addr fa = FFT::make_addr(xa, tau);
+  unsigned char *wbase = smem + C::XREGION + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
-  f2 *bufA = reinterpret_cast<f2 *>(stages + E3_STAGES * C::SLOT + (size_t)(sub * 2) * C::BUF);
-  f2 *bufB = bufA + N;
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
-  float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT + (size_t)(ROWS * 2) * C::BUF);
-  float *nb_s = pw_s + 2 * N;  // [sub][run h][tau][3]: first-channel sums of each thermal run
+  float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT);
   for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < E3_STAGES; ++i) mbar_init(&full[i], 1);
@@ -113,14 +147,14 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     const int64_t e00 = (((int64_t)p * P.nbl + b0) * P.ntime + t0) * P.nchan + P.win_start[s];
     const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
 
-    // ---- producer state (lane 0 stages rows i0 .. i0+ROWS-1 of time t) ----------
+    // ---- producer state (one elected lane stages rows i0 .. i0+ROWS-1 of time t) ----------
     int pi0 = 0;          // first row of the next step to stage
     int64_t pe = e00;     // its sample offset
     int64_t pe_t = e00;   // offset of row 0 at the producer's current time
     int pleft = nsteps;   // steps not yet staged
     auto issue = [&]() {
       if (issuer_warp && elect_one()) {
-        const int nact = min(ROWS, ng - pi0);
+        const int nact = ROWS == 1 ? 1 : min(ROWS, ng - pi0);
         mbar_expect_tx(&full[slot_p], (uint32_t)nact * (HAS_D ? ROW_BYTES : 5u * N));
         unsigned char *dst = stages + slot_p * C::SLOT;
         int64_t e = pe;
@@ -141,13 +175,14 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       --pleft;
     };
 
+    // noise multiplier per channel: sigma coefficient * sqrt(ln 2) * taper * delta_f
+    // (non-finite sigma -> 0, ds.py:3575-3582); injected noise only needs taper * delta_f
     float sigc[8];
     if (HAS_N) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (P.noise_mode == 1) {
           const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
-          // non-finite sigma -> 0 (ds.py:3575-3582); taper * delta_f folded in
           sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * tapdf[r] : 0.f;
         } else {
           sigc[r] = tapdf[r];
@@ -156,11 +191,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     }
     f2 S1[8], Sn1[8];                    // sum over the rows of a time: data and noise
     float S2[8], Sn2[8];                 // sum |x|^2
-    // thermal sums per channel, packed over adjacent channels (index 2 h + m: channels
-    // c0 + 2 m, c0 + 2 m + 1 of run h): A = sum a, B = sum a / t_int, C = sum a^2 / t_int with
-    // a = nsample^-1/2 (0 where invalid).  Rows with a valid sample next to an invalid one
-    // ("dirty" panels) additionally book what the panel mask removes into dfc[] (local memory,
-    // touched only on that rare path): per panel q, [0..2] left-end and [3..5] right-end deficits.
+    // thermal sums per channel, packed over the thread's channel pairs (tau + TPR 2m, tau + TPR (2m+1)):
+    // A = sum a, B = sum a / t_int, C = sum a^2 / t_int with a = nsample^-1/2 (0 where invalid).
+    // Rows with an invalid sample additionally book what the panel mask removes into dfc[]
+    // (local memory, touched only on that rare path): per panel q = channel tau + TPR q and its
+    // right neighbour, [0..2] left-end and [3..5] right-end deficits.
     f2 tA[4], tB[4], tC[4];
     float dfc[48];
     bool dirty_time = false;
@@ -176,7 +211,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
-    // Philox counter base of (row 0, time t0): row_id * N/2 with
+    // Philox counter base of (row 0, time t0): row_id * 3N/8 with
     // row_id = ((s npol + p) nbl_total + b) ntime_total + t   (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
                        (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
@@ -193,9 +228,25 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (HAS_N || HAS_T) tint = __ldg(P.int_time + it_off + (int64_t)ia * P.ntime);
       mbar_wait(&full[slot_c], par_c);
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
-      const f2 *vis_s = reinterpret_cast<const f2 *>(row);
-      const float *ns_s = reinterpret_cast<const float *>(row + 8 * N);
-      const unsigned char *fl_s = row + 12 * N;
+      const f2 *vis_s = reinterpret_cast<const f2 *>(row) + tau;
+      const float *ns_s = reinterpret_cast<const float *>(row + 8 * N) + tau;
+      const unsigned char *fl_s = row + 12 * N + tau;
+
+      // rt = t_int^-1/2, itv = 1 / t_int (0 where the integration time is not positive)
+      const float rt = (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
+      const float itv = rt * rt;
+      // a = nsample^-1/2 (0 where invalid): shared by the noise amplitude and the thermal sums
+      float av[8];
+      bool all_ok = true;
+      if (HAS_N || HAS_T) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float nv = ns_s[TPR * r];
+          const bool ok = active && nv > 0.f;
+          av[r] = ok ? fast_rsqrt(nv) : 0.f;
+          all_ok = all_ok && ok;
+        }
+      }
 
       // ---- data leg: (1 - flag) * taper * delta_f ; noise leg: draw * sigma(nsample, t_int) --
       f2 vd[8], vn[8];
@@ -203,23 +254,21 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
       if (HAS_N && P.noise_mode == 1) {
         float rad[8], cs[8], sn[8];
-        engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
-                          rad, cs, sn);
+        engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const bool k = active && fl_s[tau + TPR * r] == 0;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          const bool k = active && fl_s[TPR * r] == 0;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581)
-          const float tn = tint * ns_s[tau + TPR * r];
-          const float amp = (k && tn > 0.f) ? sigc[r] * rad[r] * fast_rsqrt(tn) : 0.f;
+          const float amp = (k ? sigc[r] * rt : 0.f) * (rad[r] * av[r]);
           vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
         }
       } else {
         const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const bool k = active && fl_s[tau + TPR * r] == 0;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[tau + TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          const bool k = active && fl_s[TPR * r] == 0;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           if (HAS_N) {  // injected freq-domain noise (parity mode): plain loads
             const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
             const float m = k ? sigc[r] : 0.f;
@@ -229,15 +278,15 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        if (HAS_D) TeamFftP<N>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
-        else TeamFftP<N>::run(vn, bufA, bufB, tw_s, tau, bar_id);
+        if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
+        else FFT::run(vn, fa, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           Sn1[r] = f2_add(Sn1[r], vn[r]);
           Sn2[r] = fmaf(f2_lo(vn[r]), f2_lo(vn[r]), fmaf(f2_hi(vn[r]), f2_hi(vn[r]), Sn2[r]));
         }
       } else {
-        TeamFftP<N>::run(vd, bufA, bufB, tw_s, tau, bar_id);
+        FFT::run(vd, fa, tw_s, tau, bar_id);
       }
       if (HAS_D) {
 #pragma unroll
@@ -248,53 +297,36 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
 
       if (HAS_T) {
-        // thermal sums use their own channel map: two runs of 4 consecutive channels per
-        // thread (c = 4 tau + 4 TPR h + j) -> two 128-bit loads + the right neighbours
-        const float itv = (tint > 0.f) ? 1.f / tint : 0.f;
         const f2 it2 = f2_make(itv, itv);
-        bool dirty = false;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = 4 * tau + 4 * TPR * h;
-          const float4 nv = *reinterpret_cast<const float4 *>(ns_s + c0);
-          const float n4[4] = {nv.x, nv.y, nv.z, nv.w};
-          float a4[4];
-          bool ok[5];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ok[j] = active && n4[j] > 0.f;
-            a4[j] = ok[j] ? fast_rsqrt(n4[j]) : 0.f;
-          }
-          // right neighbour of the run (no panel right of channel N - 1)
-          ok[4] = (c0 + 4 < N) ? (active && ns_s[c0 + 4] > 0.f) : ok[3];
-          dirty |= (ok[0] != ok[1]) | (ok[1] != ok[2]) | (ok[2] != ok[3]) | (ok[3] != ok[4]);
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            const f2 aa = f2_make(a4[2 * m], a4[2 * m + 1]);
-            tA[2 * h + m] = f2_add(tA[2 * h + m], aa);
-            tB[2 * h + m] = f2_fma(aa, it2, tB[2 * h + m]);
-            tC[2 * h + m] = f2_fma(f2_mul(aa, aa), it2, tC[2 * h + m]);
-          }
+        for (int m = 0; m < 4; ++m) {
+          const f2 aa = f2_make(av[2 * m], av[2 * m + 1]);
+          const f2 ab = f2_mul(aa, it2);
+          tA[m] = f2_add(tA[m], aa);
+          tB[m] = f2_add(tB[m], ab);
+          tC[m] = f2_fma(aa, ab, tC[m]);
         }
-        if (dirty) {
-          // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697):
-          // book what the full sums above contain but the panel must not
+        // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
+        // with any invalid sample books what the full sums above contain but the panel must not
+        if (team_any<TEAM>(active && !all_ok, bar_id)) {
           if (!dirty_time) {
 #pragma unroll 1
             for (int k = 0; k < 48; ++k) dfc[k] = 0.f;
             dirty_time = true;
           }
+          if (active) {
 #pragma unroll 1
-          for (int q = 0; q < 8; ++q) {
-            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
-            if (c + 1 >= N) continue;
-            const float nl = ns_s[c], nr = ns_s[c + 1];
-            if ((nl > 0.f) == (nr > 0.f)) continue;
-            const float av = fast_rsqrt(nl > 0.f ? nl : nr);
-            float *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
-            d[0] += av;
-            d[1] += av * itv;
-            d[2] += av * av * itv;
+            for (int q = 0; q < 8; ++q) {
+              const int c = tau + TPR * q;
+              if (c + 1 >= N) continue;
+              const float nl = ns_s[TPR * q], nr = ns_s[TPR * q + 1];
+              if ((nl > 0.f) == (nr > 0.f)) continue;
+              const float a1 = fast_rsqrt(nl > 0.f ? nl : nr);
+              float *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
+              d[0] += a1;
+              d[1] += a1 * itv;
+              d[2] += a1 * a1 * itv;
+            }
           }
         }
       }
@@ -324,52 +356,53 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
         }
         if (HAS_T) {
-          const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N;
-          const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N;
-          // the right end of a run's last panel is the first channel of the next thread's run
-          float *mine = nb_s + ((sub * 2) * TPR + tau) * 3;
+          const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N + tau;
+          const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N + tau;
+          // the right end of a panel is the next channel: another thread's sums, through this
+          // row's exchange buffers ((A, B) pairs in the first, C in the second)
+          team_sync<TEAM>(bar_id);  // the step's last transform reads are done
+          float Ar[8], Br[8], Cr[8], Ap[8], Bp[8], Cp[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mine[h * TPR * 3 + 0] = f2_lo(tA[2 * h]);
-            mine[h * TPR * 3 + 1] = f2_lo(tB[2 * h]);
-            mine[h * TPR * 3 + 2] = f2_lo(tC[2 * h]);
+          for (int m = 0; m < 4; ++m) {
+            Ar[2 * m] = f2_lo(tA[m]); Ar[2 * m + 1] = f2_hi(tA[m]);
+            Br[2 * m] = f2_lo(tB[m]); Br[2 * m + 1] = f2_hi(tB[m]);
+            Cr[2 * m] = f2_lo(tC[m]); Cr[2 * m + 1] = f2_hi(tC[m]);
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            sts_f2(xa + 8u * (uint32_t)(tau + TPR * r), f2_make(Ar[r], Br[r]));
+            sts_f32(xa + C::BUF + 4u * (uint32_t)(tau + TPR * r), Cr[r]);
           }
           team_sync<TEAM>(bar_id);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float nxt[3] = {0.f, 0.f, 0.f};
-            if (tau + 1 < TPR || h == 0) {
-              const float *src = (tau + 1 < TPR) ? mine + h * TPR * 3 + 3
-                                                 : nb_s + ((sub * 2 + 1) * TPR) * 3;
-              nxt[0] = src[0]; nxt[1] = src[1]; nxt[2] = src[2];
+          for (int r = 0; r < 8; ++r) {
+            if (r < 7 || tau + 1 < TPR) {  // no panel right of channel N - 1
+              const f2 nx = lds_f2(xa + 8u * (uint32_t)(tau + TPR * r + 1));
+              Ap[r] = f2_lo(nx); Bp[r] = f2_hi(nx);
+              Cp[r] = lds_f32(xa + C::BUF + 4u * (uint32_t)(tau + TPR * r + 1));
+            } else {
+              Ap[r] = Bp[r] = Cp[r] = 0.f;
             }
-            const float Ac[5] = {f2_lo(tA[2 * h]), f2_hi(tA[2 * h]), f2_lo(tA[2 * h + 1]),
-                                 f2_hi(tA[2 * h + 1]), nxt[0]};
-            const float Bc[5] = {f2_lo(tB[2 * h]), f2_hi(tB[2 * h]), f2_lo(tB[2 * h + 1]),
-                                 f2_hi(tB[2 * h + 1]), nxt[1]};
-            const float Cc[5] = {f2_lo(tC[2 * h]), f2_hi(tC[2 * h]), f2_lo(tC[2 * h + 1]),
-                                 f2_hi(tC[2 * h + 1]), nxt[2]};
+          }
+          if (dirty_time) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int q = 4 * h + j;
-              float a = Ac[j], ap = Ac[j + 1], b = Bc[j], bp = Bc[j + 1], cc = Cc[j], cp = Cc[j + 1];
-              if (dirty_time) {
-                a -= dfc[6 * q + 0]; b -= dfc[6 * q + 1]; cc -= dfc[6 * q + 2];
-                ap -= dfc[6 * q + 3]; bp -= dfc[6 * q + 4]; cp -= dfc[6 * q + 5];
-              }
-              f2 ab = f2_make(a, ap), bb = f2_make(b, bp);
-#pragma unroll
-              for (int off = TPR; off < 32; off <<= 1) {
-                ab = f2_add(ab, f2_shfl_xor(ab, off));
-                bb = f2_add(bb, f2_shfl_xor(bb, off));
-              }
-              const int c = 4 * tau + 4 * TPR * h + j;
-              const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
-              if (sub == 0)
-                th_all_acc += l * (double)f2_lo(ab) * (double)f2_lo(bb) +
-                              rr * (double)f2_hi(ab) * (double)f2_hi(bb);
-              th_auto_acc += l * (double)cc + rr * (double)cp;
+            for (int r = 0; r < 8; ++r) {
+              Ar[r] -= dfc[6 * r + 0]; Br[r] -= dfc[6 * r + 1]; Cr[r] -= dfc[6 * r + 2];
+              Ap[r] -= dfc[6 * r + 3]; Bp[r] -= dfc[6 * r + 4]; Cp[r] -= dfc[6 * r + 5];
             }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            f2 ab = f2_make(Ar[r], Ap[r]), bb = f2_make(Br[r], Bp[r]);
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              ab = f2_add(ab, f2_shfl_xor(ab, off));
+              bb = f2_add(bb, f2_shfl_xor(bb, off));
+            }
+            const double l = __ldg(wlp + TPR * r), rr = __ldg(wrp + TPR * r);
+            if (sub == 0)
+              th_all_acc += l * (double)(f2_lo(ab) * f2_lo(bb)) + rr * (double)(f2_hi(ab) * f2_hi(bb));
+            th_auto_acc += l * (double)Cr[r] + rr * (double)Cp[r];
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;

@@ -209,4 +209,116 @@ template <int N> struct TeamFftP {
   }
 };
 
+// ---- TeamFftX: the same schedule with raw shared-memory addresses ---------------------------
+// fft_pad is linear over XOR (a shift and a mask), and every index of the schedule is a per-thread
+// part plus a compile-time part on disjoint bits (base + p NS, tau + TPR r), so
+//   fft_pad(base + p NS) = fft_pad(base) ^ fft_pad(p NS).
+// With the exchange buffers aligned to their own size (8 N bytes, a power of two) the byte address
+// of an access is  (per-thread address, computed once per kernel) ^ (constant): ONE LOP3 per
+// access, shared by the two lockstep transforms (their buffers are 8 N bytes apart: an immediate).
+__device__ __forceinline__ void sts_f2(uint32_t addr, f2 v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ f2 lds_f2(uint32_t addr) {
+  f2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ void sts_f2_off(uint32_t addr, f2 v) {
+  asm volatile("st.shared.b64 [%0 + %2], %1;" ::"r"(addr), "l"(v), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ f2 lds_f2_off(uint32_t addr) {
+  f2 v;
+  asm volatile("ld.shared.b64 %0, [%1 + %2];" : "=l"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+
+template <int N> struct TeamFftX {
+  static constexpr int TPR = N / 8;
+  static constexpr int NPASS = fft_npass(N);
+  static constexpr int WORKER = TPR < 32 ? 32 : TPR;
+  static constexpr int BUFB = N * 8;               // bytes per exchange buffer (and their alignment)
+  static constexpr int NST = NPASS > 1 ? NPASS - 1 : 1;
+  struct Addr {
+    uint32_t st[NST];  // byte address of this thread's first store of pass p (every storing pass has radix 8)
+    uint32_t ld;       // byte address of this thread's first load after a pass
+  };
+  // xa: shared-space byte address of this row's buffer pair (aligned to BUFB)
+  static __device__ __forceinline__ Addr make_addr(uint32_t xa, int tau) {
+    Addr A;
+#pragma unroll
+    for (int p = 0; p < NST; ++p) {
+      const int NS = fft_ns(N, p), R = fft_radix(N, p);
+      const int base = (tau / NS) * (NS * R) + (tau % NS);
+      A.st[p] = xa + 8u * (uint32_t)fft_pad(base);
+    }
+    A.ld = xa + 8u * (uint32_t)fft_pad(tau);
+    return A;
+  }
+
+  template <int P, bool TWO>
+  static __device__ __forceinline__ void pass(f2 (&a)[8], f2 (&b)[8], const Addr &A,
+                                              const f2 *__restrict__ tw, int tau, int bar) {
+    constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
+    static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
+    if constexpr (P > 0) {
+      constexpr int OFF = fft_tw_offset(N, P);
+#pragma unroll
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+          const f2 w = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tau];
+          a[m + NB * q] = f2_cmul(a[m + NB * q], w);
+          if (TWO) b[m + NB * q] = f2_cmul(b[m + NB * q], w);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      f2 x[R], y[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        x[q] = a[m + NB * q];
+        if (TWO) y[q] = b[m + NB * q];
+      }
+      RadixP<R>::run(x);
+      if (TWO) RadixP<R>::run(y);
+      if constexpr (P < NPASS - 1) {
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          const uint32_t ad = A.st[P] ^ (8u * (uint32_t)fft_pad(p * NS));
+          sts_f2(ad, x[brev(p, LG)]);
+          if (TWO) sts_f2_off<BUFB>(ad, y[brev(p, LG)]);
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          a[m + NB * p] = x[brev(p, LG)];
+          if (TWO) b[m + NB * p] = y[brev(p, LG)];
+        }
+      }
+    }
+    if constexpr (P < NPASS - 1) {
+      team_sync<WORKER>(bar);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t ad = A.ld ^ (8u * (uint32_t)fft_pad(TPR * r));
+        a[r] = lds_f2(ad);
+        if (TWO) b[r] = lds_f2_off<BUFB>(ad);
+      }
+      if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
+      pass<P + 1, TWO>(a, b, A, tw, tau, bar);
+    }
+  }
+  // NOTE: the caller must team-sync between two calls on the same buffers (the engine's step
+  // loop does, at the top of every step).
+  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], const Addr &A,
+                                              const f2 *__restrict__ tw, int tau, int bar) {
+    pass<0, true>(a, b, A, tw, tau, bar);
+  }
+  static __device__ __forceinline__ void run(f2 (&a)[8], const Addr &A, const f2 *__restrict__ tw,
+                                             int tau, int bar) {
+    pass<0, false>(a, a, A, tw, tau, bar);
+  }
+};
+
 }  // namespace sds
