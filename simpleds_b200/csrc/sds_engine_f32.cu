@@ -96,6 +96,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   unsigned char *wbase = smem + C::XREGION + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
+  const uint32_t full_a = smem_u32(full), stages_a = smem_u32(stages);  // shared-space addresses
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
   float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT);
   for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
@@ -155,13 +156,14 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     auto issue = [&]() {
       if (issuer_warp && elect_one()) {
         const int nact = ROWS == 1 ? 1 : min(ROWS, ng - pi0);
-        mbar_expect_tx(&full[slot_p], (uint32_t)nact * (HAS_D ? ROW_BYTES : 5u * N));
-        unsigned char *dst = stages + slot_p * C::SLOT;
+        const uint32_t bar = full_a + 8u * slot_p;
+        mbar_expect_tx_a(bar, (uint32_t)nact * (HAS_D ? ROW_BYTES : 5u * N));
+        uint32_t dst = stages_a + slot_p * (uint32_t)C::SLOT;
         int64_t e = pe;
         for (int rr = 0; rr < nact; ++rr, e += row_stride, dst += C::ROWB) {
-          if (HAS_D) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot_p]);
-          tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot_p]);
-          tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot_p]);
+          if (HAS_D) tma_load_1d_a(dst, P.vis + e, 8 * N, bar);
+          tma_load_1d_a(dst + 8 * N, P.nsample + e, 4 * N, bar);
+          tma_load_1d_a(dst + 12 * N, P.flags + e, N, bar);
         }
       }
       slot_p = slot_p + 1 == E3_STAGES ? 0 : slot_p + 1;
@@ -218,15 +220,25 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
                       (uint64_t)(P.time_offset + t0));
 
     for (int k = 0; k < E3_STAGES - 1 && pleft > 0; ++k) issue();
+    // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
+    // on the critical path of every row)
+    float tint_next = 1.f;
+    if (HAS_N || HAS_T)
+      tint_next = __ldg(P.int_time + it_off + (int64_t)((ROWS == 1 || sub < ng) ? sub : 0) * P.ntime);
     for (int step = 0; step < nsteps; ++step) {
       team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
       if (pleft > 0) issue();
       const int i = ci0 + sub;
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
-      float tint = 1.f;
-      if (HAS_N || HAS_T) tint = __ldg(P.int_time + it_off + (int64_t)ia * P.ntime);
-      mbar_wait(&full[slot_c], par_c);
+      const float tint = tint_next;
+      if ((HAS_N || HAS_T) && step + 1 < nsteps) {
+        const bool wrap = ci0 + ROWS >= ng;
+        const int ni = (wrap ? 0 : ci0 + ROWS) + sub;
+        tint_next = __ldg(P.int_time + it_off + (wrap ? 1 : 0) +
+                          (int64_t)((ROWS == 1 || ni < ng) ? ni : 0) * P.ntime);
+      }
+      mbar_wait_a(full_a + 8u * slot_c, par_c);
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
       const f2 *vis_s = reinterpret_cast<const f2 *>(row) + tau;
       const float *ns_s = reinterpret_cast<const float *>(row + 8 * N) + tau;
