@@ -173,11 +173,12 @@ typedef struct sds_engine_desc {
 } sds_engine_desc;
 
 /* In-kernel noise (noise_mode 1), replacing utils.py:486-506 + ds.py:3544-3583: every
- * sample gets sigma * sqrt(-ln u1) * exp(2 pi i u2) (Box-Muller), u1 and u2 24-bit uniforms
- * cut from Philox4x32-7 words (Salmon et al. 2011) keyed by `seed`; the counter is the
- * GLOBAL sample coordinate -- row_id * 3N/8 + 3 tau + k, row_id = ((s * npol + p) *
- * nbl_total + bl_offset + b) * ntime_total + time_offset + t -- so the realisation does not
- * depend on batching or sharding (exact word-to-channel map: oracle/engine_ref.py).
+ * sample gets sigma * sqrt(-ln u1) * exp(2 pi i u2) (Box-Muller), u1 and u2 23-bit uniforms
+ * cut from Philox4x32-7 words (Salmon et al. 2011) keyed by `seed`; the 128-bit counter is the
+ * GLOBAL sample coordinate -- (row_id low word, row_id high word, 3 tau + k, 0) for power-of-two
+ * windows, row_id = ((s * npol + p) * nbl_total + bl_offset + b) * ntime_total + time_offset + t
+ * -- so the realisation does not depend on batching or sharding (exact word-to-channel map:
+ * oracle/engine_ref.py).
  *
  * Inputs: vis  c64 [nuv][npol][nbl][ntime][nchan]; flags u8, nsample f32 same
  * shape; int_time f32 [nbl][ntime]; group_offset int32[ngroup+1];

@@ -75,8 +75,8 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
     sigma * sqrt(-ln u1) * exp(2 pi i u2), in float32 like the kernel (sds_engine_f32.cu).
 
     sigma_coef32 (S,P,N) float32; nsample (P,B,T,F0) float32; int_time (B,T) float32.
-    A row (s,p,b,t) of N samples consumes 3N/8 Philox4x32-7 calls, counter =
-    row_id * 3N/8 + 3 tau + k (k = 0..2), row_id = ((s*P + p)*Bt + b)*Tt + t; thread tau
+    A row (s,p,b,t) of N samples consumes 3N/8 Philox4x32-7 calls, 128-bit counter =
+    (row_id low word, row_id high word, 3 tau + k, 0) (k = 0..2), row_id = ((s*P + p)*Bt + b)*Tt + t; thread tau
     owns channels tau + (N/8) r, r = 0..7, and cuts its 12 words W into eight 46-bit draws
     (23-bit radius field, 23-bit angle field): for the pair (r = 2m, 2m + 1), (w0, w1, w2) = W[3m..3m+2],
       even: rad = w0[22:0],   ang = w1[22:0]
@@ -93,9 +93,9 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
               + (b_i + bl_offset).astype(np.uint64)) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
     words = []
     for k in range(3):
-        ctr = row_id * np.uint64(3 * tpr) + np.uint64(3) * tau_i.astype(np.uint64) + np.uint64(k)
+        ctr = row_id
         words += list(philox4x32((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
-                                 np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
+                                 (3 * tau_i + k).astype(np.uint32), np.zeros(ctr.shape, np.uint32),
                                  np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
                                  rounds=ENGINE_PHILOX_ROUNDS))
     W = [w.astype(np.uint32) for w in words]  # 12 arrays (S,P,B,T,tpr)

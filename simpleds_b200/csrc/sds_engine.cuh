@@ -186,9 +186,10 @@ __device__ __forceinline__ float fast_cos(float x) {
 }
 // Eight unit draws of the thread that owns channels tau + TPR r (r = 0..7) of row `row_id`:
 // rad2 = sqrt(-log2 u1) (the caller folds sqrt(ln 2) into its amplitude), (cs, sn) =
-// exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox calls, counter =
-// row_id * 3N/8 + 3 tau + k; the thread's 12 words are cut into eight 46-bit draws (23-bit
-// radius uniform, 23-bit angle).  Each field is OR-ed under the exponent of 1.0f (one LOP3 builds
+// exp(2 pi i u2).  A row of N = 8 TPR draws takes 3N/8 Philox calls; the 128-bit counter of call
+// k = 0..2 of thread tau is (row_id low word, row_id high word, 3 tau + k, 0) -- no per-row 64-bit
+// counter arithmetic, and the first round's product with the row words serves all three calls.
+// The thread's 12 words are cut into eight 46-bit draws (23-bit radius uniform, 23-bit angle).  Each field is OR-ed under the exponent of 1.0f (one LOP3 builds
 // the float f in [1, 2), no integer conversion): u1 = 2 - f in (0, 1], angle = 2 pi f (mod 2 pi).
 // Per word triple (w0, w1, w2) = W[3m .. 3m+2], draws r = 2m (even) and 2m + 1 (odd):
 //   even: radius field w0[22:0],  angle field w1[22:0]
@@ -202,12 +203,11 @@ __device__ __forceinline__ float unit_float_23(uint32_t bits) {  // [1, 2) from 
 template <int TPR>
 __device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, const uint32_t (&key)[16],
                                              float (&rad2)[8], float (&cs)[8], float (&sn)[8]) {
-  const uint64_t ctr0 = row_id * (uint64_t)(3 * TPR) + (uint64_t)(3 * tau);
   uint32_t W[12];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const uint64_t ctr = ctr0 + (uint64_t)k;
-    const u32x4 rn = philox4x32_keyed<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, key);
+    const u32x4 rn = philox4x32_keyed<ENG_PHILOX_ROUNDS>(
+        {(uint32_t)row_id, (uint32_t)(row_id >> 32), (uint32_t)(3 * tau + k), 0u}, key);
     W[4 * k] = rn.x; W[4 * k + 1] = rn.y; W[4 * k + 2] = rn.z; W[4 * k + 3] = rn.w;
   }
 #pragma unroll

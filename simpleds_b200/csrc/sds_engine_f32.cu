@@ -177,17 +177,17 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       --pleft;
     };
 
-    // noise multiplier per channel: sigma coefficient * sqrt(ln 2) * taper * delta_f
-    // (non-finite sigma -> 0, ds.py:3575-3582); injected noise only needs taper * delta_f
+    // noise multiplier per channel on top of the data's mask * taper * delta_f: sigma coefficient
+    // * sqrt(ln 2) (non-finite sigma -> 0, ds.py:3575-3582); 1 for injected noise
     float sigc[8];
     if (HAS_N) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (P.noise_mode == 1) {
           const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
-          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * tapdf[r] : 0.f;
+          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 : 0.f;
         } else {
-          sigc[r] = tapdf[r];
+          sigc[r] = 1.f;
         }
       }
     }
@@ -213,7 +213,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
-    // Philox counter base of (row 0, time t0): row_id * 3N/8 with
+    // Philox counter words 0, 1 of (row 0, time t0):
     // row_id = ((s npol + p) nbl_total + b) ntime_total + t   (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
                        (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
@@ -269,21 +269,20 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const bool k = active && fl_s[TPR * r] == 0;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          const float m = (active && fl_s[TPR * r] == 0) ? tapdf[r] : 0.f;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, m);
           // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581)
-          const float amp = (k ? sigc[r] * rt : 0.f) * (rad[r] * av[r]);
+          const float amp = (m * (sigc[r] * rt)) * (rad[r] * av[r]);
           vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
         }
       } else {
         const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const bool k = active && fl_s[TPR * r] == 0;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          const float m = (active && fl_s[TPR * r] == 0) ? tapdf[r] : 0.f;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, m);
           if (HAS_N) {  // injected freq-domain noise (parity mode): plain loads
             const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
-            const float m = k ? sigc[r] : 0.f;
             vn[r] = f2_make(c.x * m, c.y * m);
           }
         }

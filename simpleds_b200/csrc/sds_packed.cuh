@@ -263,11 +263,14 @@ template <int N> struct TeamFftX {
     static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
     if constexpr (P > 0) {
       constexpr int OFF = fft_tw_offset(N, P);
+      // the twiddle of butterfly j depends on j % NS only: with NS < TPR the lanes of a warp read
+      // NS distinct words (a broadcast: fewer shared-memory wavefronts than TPR distinct ones)
+      const int tt = (NB == 1 && NS < TPR) ? (tau & (NS - 1)) : tau;
 #pragma unroll
       for (int m = 0; m < NB; ++m)
 #pragma unroll
         for (int q = 1; q < R; ++q) {
-          const f2 w = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tau];
+          const f2 w = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tt];
           a[m + NB * q] = f2_cmul(a[m + NB * q], w);
           if (TWO) b[m + NB * q] = f2_cmul(b[m + NB * q], w);
         }
