@@ -128,8 +128,9 @@ def engine_noise_freq_chirpz(sigma_coef32, nsample, int_time, win_start, nfreq, 
     """The noise of the chirp-z engine (window lengths that are not powers of two,
     sds_engine_blue.cu): convolution length M = smallest power of two >= max(64, 2N - 1), row
     team of TPR = M / 8 threads; thread tau draws channels tau + TPR r (r < 4) from two
-    Philox4x32-7 calls, counter = row_id * 2 TPR + 2 tau + k: word 2r is the 32-bit radius
-    uniform, word 2r + 1 the angle."""
+    Philox4x32-7 calls, counter = (row_id low word, row_id high word, 2 tau + k, 0): the low 23
+    bits of word 2r are the radius field, those of word 2r + 1 the angle field (f = 1 + field 2^-23,
+    u1 = 2 - f, angle = 2 pi f, as in engine_noise_freq)."""
     P, B, T, _ = nsample.shape
     S, N = len(win_start), nfreq
     M = 64
@@ -144,9 +145,9 @@ def engine_noise_freq_chirpz(sigma_coef32, nsample, int_time, win_start, nfreq, 
               + (b_i + bl_offset).astype(np.uint64)) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
     W = []
     for k in range(2):
-        ctr = row_id * np.uint64(2 * tpr) + np.uint64(2) * tau_i.astype(np.uint64) + np.uint64(k)
+        ctr = row_id
         W += list(philox4x32((ctr & _LO).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
-                             np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32),
+                             (2 * tau_i + k).astype(np.uint32), np.zeros(ctr.shape, np.uint32),
                              np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
                              rounds=ENGINE_PHILOX_ROUNDS))
     rad = np.zeros((S, P, B, T, 4 * tpr), np.uint32)
@@ -157,9 +158,10 @@ def engine_noise_freq_chirpz(sigma_coef32, nsample, int_time, win_start, nfreq, 
         ang[..., ch] = W[2 * r + 1]
     rad, ang = rad[..., :N], ang[..., :N]
     f32 = np.float32
-    u1 = (rad.astype(f32) * f32(2.0 ** -32) + f32(2.0 ** -33)).astype(f32)
+    m23 = np.uint32(0x7FFFFF)
+    u1 = (f32(2.0) - (f32(1.0) + (rad & m23).astype(f32) * f32(2.0 ** -23))).astype(f32)  # exact
     w = (-np.log(u1.astype(np.float64))).astype(f32)
-    a = (ang.astype(f32) * f32(2 * np.pi / 2.0 ** 32)).astype(np.float64)
+    a = ((f32(1.0) + (ang & m23).astype(f32) * f32(2.0 ** -23)) * f32(6.2831853071795865)).astype(f32).astype(np.float64)
     chans = np.asarray(win_start)[:, None] + np.arange(N)
     ns_w = np.stack([nsample[..., chans[s]] for s in range(S)])
     tn = int_time[None, None, :, :, None].astype(f32) * ns_w.astype(f32)

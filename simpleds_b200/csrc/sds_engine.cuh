@@ -128,23 +128,6 @@ template <> __device__ __forceinline__ double rsqrt_t<double>(float x) { return 
 #ifndef ENG_PHILOX_ROUNDS
 #define ENG_PHILOX_ROUNDS 7  // smallest Crush-resistant Philox4x32 (Salmon et al. 2011, table 2)
 #endif
-template <int ROUNDS>
-__device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
-    u32x4 n;
-    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
-    n.y = (uint32_t)p1;
-    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
-    n.w = (uint32_t)p0;
-    c = n;
-    k0 += W0;
-    k1 += W1;
-  }
-  return c;
-}
 // Philox4x32 with the round keys taken from the kernel parameters (constant bank operands:
 // no key-schedule arithmetic in the loop)
 template <int ROUNDS>
@@ -239,24 +222,25 @@ int run_engine_f32(int N, const EngineParams &P, int legs, cudaStream_t st, int 
 int run_engine_blue(int M, const EngineParams &P, int legs, cudaStream_t st, int *launches);
 
 // Four unit draws of the thread that owns channels tau + TPR r (r = 0..3) of row `row_id` in the
-// chirp-z engine (N <= 4 TPR): two Philox calls, counter = row_id * 2 TPR + 2 tau + k; draw r
-// takes word 2r for the radius (32-bit uniform) and word 2r + 1 for the angle.
+// chirp-z engine (N <= 4 TPR): two Philox calls, counter = (row_id low word, row_id high word,
+// 2 tau + k, 0); draw r takes word 2r for the radius field and word 2r + 1 for the angle field
+// (low 23 bits each, under the exponent of 1.0f as in engine_draw8).
 template <int TPR>
-__device__ __forceinline__ void engine_draw4(uint64_t row_id, int tau, uint32_t k0, uint32_t k1,
+__device__ __forceinline__ void engine_draw4(uint64_t row_id, int tau, const uint32_t (&key)[16],
                                              float (&rad2)[4], float (&cs)[4], float (&sn)[4]) {
-  const uint64_t ctr0 = row_id * (uint64_t)(2 * TPR) + (uint64_t)(2 * tau);
   uint32_t W[8];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const uint64_t ctr = ctr0 + (uint64_t)k;
-    const u32x4 rn = philox4x32<ENG_PHILOX_ROUNDS>({(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
+    const u32x4 rn = philox4x32_keyed<ENG_PHILOX_ROUNDS>(
+        {(uint32_t)row_id, (uint32_t)(row_id >> 32), (uint32_t)(2 * tau + k), 0u}, key);
     W[4 * k] = rn.x; W[4 * k + 1] = rn.y; W[4 * k + 2] = rn.z; W[4 * k + 3] = rn.w;
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const float u1 = fmaf((float)W[2 * r], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    rad2[r] = fast_sqrt(-__log2f(u1));
-    __sincosf((float)W[2 * r + 1] * 1.4629180792671596e-9f, &sn[r], &cs[r]);  // 2 pi / 2^32
+    rad2[r] = fast_sqrt(-fast_lg2(2.0f - unit_float_23(W[2 * r])));
+    const float ang = unit_float_23(W[2 * r + 1]) * 6.2831853071795865f;
+    cs[r] = fast_cos(ang);
+    sn[r] = fast_sin(ang);
   }
 }
 

@@ -29,10 +29,12 @@ template <int M> struct EBCfg {
   static constexpr int ROWB = 13 * NPMAX;                // vis 8 NP | nsample 4 NP | flags NP
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = M * 8;
+  static constexpr int XREGION = NWORKER * ROWS * 2 * BUF;  // all exchange buffers, aligned to BUF
   static constexpr int TW_BYTES = ((fft_tw_total(M) * 8 + 127) / 128) * 128;
-  // per worker: 64 B barriers | EB_STAGES slots | ROWS * 2 exchange buffers | 2 * 4 TPR floats
-  static constexpr int WORKER_BYTES = 64 + EB_STAGES * SLOT + ROWS * 2 * BUF + 32 * TPR;
-  static constexpr int SMEM = TW_BYTES + NWORKER * WORKER_BYTES;
+  // per worker: 64 B barriers | EB_STAGES slots | 2 * 4 TPR floats
+  static constexpr int WORKER_BYTES = 64 + EB_STAGES * SLOT + 32 * TPR;
+  // BUF bytes of slack in front: the exchange region is aligned to BUF at run time (TeamFftX)
+  static constexpr int SMEM = BUF + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
 
 __device__ __forceinline__ f2 f2_conj(f2 a) { return f2_make(f2_lo(a), -f2_hi(a)); }
@@ -42,21 +44,24 @@ __global__ void __launch_bounds__(EBCfg<M>::THREADS, EBCfg<M>::MINB)
 engine_blue_kernel(const __grid_constant__ EngineParams P) {
   constexpr bool HAS_N = (LEGS & LEG_NOISE) != 0, HAS_T = (LEGS & LEG_THERMAL) != 0;
   using C = EBCfg<M>;
+  using FFT = TeamFftX<M>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t s0 = smem_u32(smem_raw);
+  unsigned char *smem = smem_raw + (((s0 + C::BUF - 1u) & ~(uint32_t)(C::BUF - 1)) - s0);
 
-  f2 *tw_s = reinterpret_cast<f2 *>(smem);
+  f2 *tw_s = reinterpret_cast<f2 *>(smem + C::XREGION);
   for (int i = threadIdx.x; i < fft_tw_total(M); i += C::THREADS)
     tw_s[i] = reinterpret_cast<const f2 *>(P.blue_tw)[i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;
-  unsigned char *wbase = smem + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
+  const uint32_t xa = smem_u32(smem) + (uint32_t)((wid * ROWS + sub) * 2) * C::BUF;
+  const typename FFT::Addr fa = FFT::make_addr(xa, tau);
+  unsigned char *wbase = smem + C::XREGION + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
-  f2 *bufA = reinterpret_cast<f2 *>(stages + EB_STAGES * C::SLOT + (size_t)(sub * 2) * C::BUF);
-  f2 *bufB = bufA + M;
   // per-worker sums over times of |S1|^2: [0, 4 TPR) data, [4 TPR, 8 TPR) noise
-  float *pw_s = reinterpret_cast<float *>(stages + EB_STAGES * C::SLOT + (size_t)(ROWS * 2) * C::BUF);
+  float *pw_s = reinterpret_cast<float *>(stages + EB_STAGES * C::SLOT);
   for (int i = tl; i < 8 * TPR; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < EB_STAGES; ++i) mbar_init(&full[i], 1);
@@ -194,8 +199,7 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
       for (int r = 4; r < 8; ++r) vd[r] = vn[r] = 0ull;  // zero padding of the convolution
       float rad2[4], cs[4], sn[4];
       if (HAS_N && P.noise_mode == 1)
-        engine_draw4<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.seed_lo, P.seed_hi,
-                          rad2, cs, sn);
+        engine_draw4<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad2, cs, sn);
       const int64_t e_in = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -236,20 +240,20 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
 
       // chirp-z: FFT_M, multiply by the transform of the wrapped chirp, inverse FFT_M
       if (HAS_N) {
-        TeamFftP<M>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
+        FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           vd[r] = f2_conj(f2_cmul(vd[r], bh[r]));
           vn[r] = f2_conj(f2_cmul(vn[r], bh[r]));
         }
         team_sync<TEAM>(bar_id);
-        TeamFftP<M>::run2(vd, vn, bufA, bufB, tw_s, tau, bar_id);
+        FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
       } else {
-        TeamFftP<M>::run(vd, bufA, bufB, tw_s, tau, bar_id);
+        FFT::run(vd, fa, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) vd[r] = f2_conj(f2_cmul(vd[r], bh[r]));
         team_sync<TEAM>(bar_id);
-        TeamFftP<M>::run(vd, bufA, bufB, tw_s, tau, bar_id);
+        FFT::run(vd, fa, tw_s, tau, bar_id);
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {  // X[k] = c[k] / M * conj(.)   (zero beyond N: cout = 0)
