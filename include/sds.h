@@ -204,6 +204,40 @@ int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void
 /* number of kernel launches the last sds_engine_run on this thread enqueued */
 int sds_engine_last_launches(void);
 
+/* ---- downstream estimators on the (averaged) spectra: SURVEY 8(f3) ----------------------
+ * All arrays are C-ordered and viewed as (outer, n, inner) around the reduced / folded /
+ * resampled axis; values are fp64 (real) or complex128 (interleaved, dtype = SDS_F64 / SDS_C128). */
+
+/* utils.py:569-645 weighted_average: out[o,i] = sum_k w x / sum_k w,
+ * out_sigma[o,i] = sqrt(sum_k sigma^2 |w|^2 / |sum_k w|^2), real fp64.
+ * weights: NULL -> inverse variance 1 / sigma^2 (utils.py:628-629); weights_1d != 0 -> one weight
+ * per position of the averaged axis (n values), else the shape of x. */
+int sds_weighted_average(const double *x, const double *sigma, const double *weights,
+                         int weights_1d, int64_t outer, int64_t n, int64_t inner, double *out,
+                         double *out_sigma, sds_stream stream);
+
+/* utils.py:651-796 fold_along_delay: output bin j (0 <= j < nout) is the weighted average of the
+ * input bins pos0 + j and neg0 - j along the folded axis (the host side derives pos0 / neg0 from
+ * the delays exactly as utils.py:721-761 split the array); with zero_bin != 0 bin j = 0 is the
+ * shared delay = 0 bin, whose uncertainty is scaled by sqrt(2) before the average
+ * (utils.py:733-737).  dtype SDS_F64: real values, uncertainties and weights.  dtype SDS_C128:
+ * real and imaginary parts are folded separately with the real / imaginary parts of the
+ * weights (utils.py:778-794).  weights == NULL -> ones (real) / 1 + 1j (complex). */
+int sds_fold_along_delay(const void *x, const void *sigma, const void *weights, int dtype,
+                         int64_t outer, int64_t n, int64_t inner, int64_t pos0, int64_t neg0,
+                         int64_t nout, int zero_bin, void *out, void *out_sigma,
+                         sds_stream stream);
+
+/* utils.py:171-209 bootstrap_array, the gather (np.take with an (n, nboot) index table):
+ * out[o, i, b, :] = in[o, index[i * nboot + b], :], elem_bytes bytes per element (8 or 16). */
+int sds_bootstrap_gather(const void *in, const int64_t *index, int elem_bytes, int64_t outer,
+                         int64_t n, int64_t nboot, int64_t inner, void *out, sds_stream stream);
+/* ... and the index table itself, index[i * nboot + b] uniform in [0, n): Philox4x32-10 keyed by
+ * `seed`, counter = flat position / 4 (the reference draws from numpy's global MT19937,
+ * utils.py:205-207; injected indices give bit-level parity, this gives a reproducible stream). */
+int sds_bootstrap_indices(uint64_t seed, int64_t n, int64_t nboot, int64_t *index,
+                          sds_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ _SIGNATURES = {
     "sds_engine_workspace_bytes": (_i64, [_vp, C.POINTER(EngineDesc)]),
     "sds_engine_run": (_i32, [_vp, C.POINTER(EngineDesc)] + [_vp] * 17 + [_vp]),
     "sds_engine_last_launches": (_i32, []),
+    "sds_weighted_average": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "sds_fold_along_delay": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
+                                    _vp, _vp, _vp]),
+    "sds_bootstrap_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "sds_bootstrap_indices": (_i32, [_u64, _i64, _i64, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -274,3 +274,65 @@ def thermal_power_sums(n1, n2, coef, freq, int_time, pol_factor, group_offset=No
         "sds_thermal_power_avg",
     )
     return out_all, out_auto
+
+
+# ---- downstream estimators ------------------------------------------------
+def _outer_n_inner(shape, axis):
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    return outer, int(shape[axis]), inner
+
+
+def weighted_average(x, sigma, weights, axis):
+    """x, sigma: float64 CUDA tensors of one shape; weights: None, 1-D (n,) or the shape of x."""
+    x, sigma = x.contiguous(), sigma.contiguous()
+    outer, n, inner = _outer_n_inner(x.shape, axis)
+    oshape = tuple(x.shape[:axis]) + tuple(x.shape[axis + 1:])
+    out = torch.empty(oshape, dtype=torch.float64, device=x.device)
+    osig = torch.empty_like(out)
+    w1d = 0
+    if weights is not None:
+        weights = weights.contiguous()
+        w1d = 1 if weights.dim() == 1 and x.dim() != 1 else 0
+    rc = _lib.load().sds_weighted_average(_lib.ptr(x), _lib.ptr(sigma), _lib.ptr(weights), w1d, outer,
+                                          n, inner, _lib.ptr(out), _lib.ptr(osig), _lib.stream_ptr())
+    _lib.check(rc, "sds_weighted_average")
+    return out, osig
+
+
+def fold_along_delay(x, sigma, weights, axis, pos0, neg0, nout, zero_bin):
+    """x, sigma, weights: CUDA tensors of one shape and dtype (float64 or complex128)."""
+    x, sigma = x.contiguous(), sigma.contiguous()
+    code = _lib.SDS_C128 if x.is_complex() else _lib.SDS_F64
+    outer, n, inner = _outer_n_inner(x.shape, axis)
+    oshape = tuple(x.shape[:axis]) + (nout,) + tuple(x.shape[axis + 1:])
+    out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    osig = torch.empty_like(out)
+    if weights is not None:
+        weights = weights.contiguous()
+    rc = _lib.load().sds_fold_along_delay(_lib.ptr(x), _lib.ptr(sigma), _lib.ptr(weights), code, outer, n,
+                                          inner, int(pos0), int(neg0), int(nout), int(bool(zero_bin)),
+                                          _lib.ptr(out), _lib.ptr(osig), _lib.stream_ptr())
+    _lib.check(rc, "sds_fold_along_delay")
+    return out, osig
+
+
+def bootstrap_indices(n, nboot, seed):
+    idx = torch.empty((n, nboot), dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    rc = _lib.load().sds_bootstrap_indices(int(seed) & 0xFFFFFFFFFFFFFFFF, int(n), int(nboot), _lib.ptr(idx),
+                                           _lib.stream_ptr())
+    _lib.check(rc, "sds_bootstrap_indices")
+    return idx
+
+
+def bootstrap_gather(x, index, axis):
+    """x: float64 / complex128 CUDA tensor; index: int64 (n, nboot) CUDA tensor."""
+    x, index = x.contiguous(), index.contiguous()
+    outer, n, inner = _outer_n_inner(x.shape, axis)
+    nboot = int(index.shape[1])
+    oshape = tuple(x.shape[:axis]) + (n, nboot) + tuple(x.shape[axis + 1:])
+    out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    rc = _lib.load().sds_bootstrap_gather(_lib.ptr(x), _lib.ptr(index), x.element_size(), outer, n, nboot,
+                                          inner, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "sds_bootstrap_gather")
+    return out

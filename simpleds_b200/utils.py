@@ -178,3 +178,184 @@ def jy_to_mk(freqs):
         freqs = freqs.value
     freqs = np.asarray(freqs, dtype=np.float64)
     return Quantity(1e-23 * C_M_PER_S**2 / (2.0 * freqs**2 * K_B_J_PER_K), "mK sr Jy^-1")
+
+
+# ---- downstream estimators on the averaged spectra ---------------------------
+def bootstrap_array(array, nboot=100, axis=0, seed=None, indices=None):
+    """utils.py:171-209: resample with replacement along ``axis``; the output gains an axis of
+    length ``nboot`` right after it.
+
+    The reference draws the (n, nboot) index table from numpy's global generator; here it comes
+    from Philox4x32-10 on the device (``seed``; a fresh stream per call when omitted) or is
+    injected with ``indices`` for bit-level parity tests.  The gather runs in libsds.so."""
+    value, unit, was_numpy = _split(array)
+    if axis >= len(value.shape):
+        raise ValueError(
+            "Specified axis must be shorter than the length "
+            "of input array.\n"
+            "axis value was {0} but array has {1} dimensions".format(axis, len(value.shape))
+        )
+    axis = axis % len(value.shape)
+    n = int(value.shape[axis])
+    t = _to_device(value)
+    if not t.is_complex():
+        t = t.to(torch.float64)
+    elif t.dtype != torch.complex128:
+        t = t.to(torch.complex128)
+    if indices is None:
+        if seed is None:
+            seed = 0xB007 + next(_noise_calls)
+        idx = ops.bootstrap_indices(n, int(nboot), seed)
+    else:
+        idx = torch.as_tensor(np.asarray(indices), device=t.device).to(torch.int64)
+        if tuple(idx.shape) != (n, int(nboot)):
+            raise ValueError(f"indices must have shape ({n}, {int(nboot)}), got {tuple(idx.shape)}")
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n):
+            raise ValueError("indices out of range for the resampled axis")
+    out = ops.bootstrap_gather(t, idx, axis)
+    return _wrap(out, unit, was_numpy, is_quantity(array))
+
+
+def weighted_average(array, uncertainty, weights=None, axis=-1):
+    """utils.py:569-645: weighted average along ``axis`` and the propagated uncertainty
+    (inverse-variance weights when ``weights`` is None)."""
+    if is_quantity(array):
+        if is_quantity(uncertainty):
+            if not uncertainty.unit == array.unit:
+                raise ValueError(  # astropy raises UnitConversionError (a ValueError) here
+                    f"'{uncertainty.unit}' and '{array.unit}' are not convertible"
+                )
+        else:
+            raise ValueError(
+                "Input array is a Quantity Object but "
+                "uncertainty is not. Either both arrays must be "
+                "Quantity objects or neither must be."
+            )
+    elif is_quantity(uncertainty):
+        raise ValueError(
+            "Input array is a not Quantity Objcet but "
+            "uncertainty is. Either both arrays must be "
+            "Quantity objects or neither must be."
+        )
+    value, unit, was_numpy = _split(array)
+    sig, _, _ = _split(uncertainty)
+    if not tuple(value.shape) == tuple(sig.shape):
+        raise ValueError(
+            "Input array and uncertainties must have the same "
+            "shape. Array shape: {array}, Uncertainty shape: "
+            "{error}".format(array=tuple(value.shape), error=tuple(sig.shape))
+        )
+    w = None
+    if weights is not None:
+        w, _, _ = _split(weights)
+        if len(w.shape) == 1 and int(np.prod(w.shape)) != value.shape[axis]:
+            raise ValueError(
+                "1-Dimenionals weights must have the same shape "
+                "as the axis over which the average is taken."
+            )
+        elif not tuple(w.shape) == tuple(value.shape):  # (sic) utils.py:636: also 1-D weights of N-D input
+            raise ValueError(
+                "Input array and uncertainties must have the same "
+                "shape. Array shape: {array}, Uncertainty shape: "
+                "{weights}".format(array=tuple(value.shape), weights=tuple(w.shape))
+            )
+        w = _to_device(w).to(torch.float64)
+    axis = axis % len(value.shape)
+    out, osig = ops.weighted_average(_to_device(value).to(torch.float64), _to_device(sig).to(torch.float64),
+                                     w, axis)
+    q = is_quantity(array)
+    return _wrap(out, unit, was_numpy, q), _wrap(osig, unit, was_numpy, q)
+
+
+_FOLD_UNITS = (Unit("mK^2 Mpc^3"), Unit("mK^2 Mpc^3 littleh^-3"), Unit("s"))
+
+
+def fold_along_delay(delays, array, uncertainty, weights=None, axis=-1):
+    """utils.py:651-796: average the bins of equal |delay| along ``axis``.
+
+    ``delays`` and ``array`` must be Quantities (time; power or time), as the reference's
+    ``quantity_input`` demands.  The split of the axis follows utils.py:730-770 line by line on
+    the host (it is index arithmetic on the 1-D delays); the two-point weighted average and the
+    uncertainty propagation of every bin run in libsds.so.  Unlike the reference (which indexes
+    the 1-D delays with the array's axis, so that only axis = -1 / 0 work) any axis is folded."""
+    if not is_quantity(delays) or not delays.unit == Unit("s"):
+        raise TypeError("Argument 'delays' to function 'fold_along_delay' must be a time Quantity")
+    if not is_quantity(array) or not array.unit.is_equivalent(_FOLD_UNITS):
+        raise TypeError("Argument 'array' to function 'fold_along_delay' must be in one of "
+                        "mK^2*Mpc^3, mK^2*Mpc^3/littleh^3, time")
+    d = np.asarray(delays.value.cpu() if isinstance(delays.value, torch.Tensor) else delays.value, dtype=np.float64)
+    value, unit, was_numpy = _split(array)
+    sig, _, _ = _split(uncertainty)
+    n = len(d)
+    if value.shape[axis] != n:
+        raise ValueError(
+            "Input array must have same length as the "
+            "delays along the specified axis."
+            "Axis given was {0}, the array has length {1} "
+            "but delays are length {2}".format(axis, value.shape[axis], n)
+        )
+    if n % 2 != 0 and np.abs(d).min() != 0:
+        raise ValueError(
+            "Input delays must have either a delay=0 bin "
+            "as the central value or have an even size."
+        )
+    if not tuple(value.shape) == tuple(sig.shape):
+        raise ValueError(
+            "Input array and uncertainties must have the same "
+            "shape. Array shape: {array}, Uncertainty shape: "
+            "{error}".format(array=tuple(value.shape), error=tuple(sig.shape))
+        )
+    axis = axis % len(value.shape)
+    x = _to_device(value)
+    s = _to_device(sig)
+    is_cplx = bool(x.is_complex() and bool(torch.any(x.imag != 0)))
+    # split of the axis, utils.py:730-770
+    if np.abs(d).min() == 0 and n % 2:
+        z = int(np.argmin(np.abs(d)))
+        pos0, neg0, nout, zero_bin = z, z, n - z, True
+        if n - z != z + 1:
+            raise ValueError("all input arrays must have the same shape")  # np.stack, utils.py:772
+    else:
+        idx = np.where(np.logical_and(d >= 0, np.abs(d) == np.abs(d).min()))[0]
+        if idx.size != 1:
+            raise ValueError("Input delays must split into a negative and a non-negative half")
+        sp = int(idx[0])
+        pos0, neg0, nout, zero_bin = sp, sp - 1, n - sp, False
+        if n - sp != sp:
+            raise ValueError("all input arrays must have the same shape")  # np.stack, utils.py:772
+    w = None
+    if weights is not None:
+        wv, _, _ = _split(weights)
+        w = _to_device(wv)
+        if tuple(w.shape) != tuple(x.shape):
+            raise ValueError(
+                "Input array and uncertainties must have the same "
+                "shape. Array shape: {array}, Uncertainty shape: "
+                "{weights}".format(array=tuple(x.shape), weights=tuple(w.shape))
+            )
+    if not is_cplx:  # utils.py:776-779: real parts, weights as given
+        xr = (x.real if x.is_complex() else x).to(torch.float64)
+        sr = (s.real if s.is_complex() else s).to(torch.float64)
+        if w is not None and w.is_complex():
+            if bool(torch.any(w.imag != 0)):
+                raise ValueError("complex weights need complex values (np.average of real values with "
+                                 "complex weights is not supported by the device path)")
+            w = w.real
+        wr = None if w is None else w.to(torch.float64)
+        out, osig = ops.fold_along_delay(xr, sr, wr, axis, pos0, neg0, nout, zero_bin)
+    else:  # utils.py:780-794: real and imaginary parts with the real / imaginary weights
+        xc = x.to(torch.complex128)
+        sc = s.to(torch.complex128)
+        if w is None:
+            wc = None  # the kernel's default is 1 + 1j
+        else:
+            if w.is_complex():
+                wc = w.to(torch.complex128)
+                if not bool(torch.any(wc.imag != 0)):
+                    wc = torch.complex(wc.real, torch.ones_like(wc.real))
+            else:
+                # (sic) utils.py:784-787: real weights are cast to complex64 -- single precision
+                w32 = w.to(torch.float64).to(torch.float32).to(torch.float64)
+                wc = torch.complex(w32, torch.ones_like(w32))
+        out, osig = ops.fold_along_delay(xc, sc, wc, axis, pos0, neg0, nout, zero_bin)
+    return _wrap(out, unit, was_numpy, True), _wrap(osig, unit, was_numpy, True)
