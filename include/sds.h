@@ -238,6 +238,31 @@ int sds_bootstrap_gather(const void *in, const int64_t *index, int elem_bytes, i
 int sds_bootstrap_indices(uint64_t seed, int64_t n, int64_t nboot, int64_t *index,
                           sds_stream stream);
 
+/* ---- cosmological normalisation: SURVEY 8(f1) ---------------------------------------------
+ * The flat-LambdaCDM background the reference gets from astropy (cosmo.py:20: Planck15), as plain
+ * numbers: Ode0 = 1 - Om0 - Ogamma0 - Onu0 already evaluated by the caller. */
+#define SDS_COSMO_MAX_NU 4
+typedef struct sds_cosmo_params {
+  double h0_km_s_mpc, om0, ode0, ogamma0;
+  double neff_per_nu;       /* Neff / number of neutrino species                          */
+  double nmassless_nu;      /* number of massless species                                 */
+  double nu_y[SDS_COSMO_MAX_NU]; /* m_nu c^2 / (k_B T_nu0) of the massive species          */
+  int32_t nmassive_nu;
+  int32_t has_massive_nu_or_radiation; /* 0: Tcmb0 == 0, no radiation terms at all        */
+} sds_cosmo_params;
+/* E(z) (astropy FlatLambdaCDM.efunc, used at cosmo.py:131, 157, 183) and the line-of-sight
+ * comoving distance in Mpc (= comoving_transverse_distance for a flat universe, cosmo.py:77,
+ * 105, 182) at n redshifts; either output may be NULL. */
+int sds_cosmo_evaluate(const sds_cosmo_params *params, const double *z, int64_t n,
+                       double *efunc_out, double *comoving_distance_mpc_out, sds_stream stream);
+/* delay_spectrum.py:1260-1268 / 1286-1297 / 1318-1330: out[s,p] = trapz over the window's
+ * frequencies of  freq^freq_power / x2y * taper^2 * beam_sq_area,  freq and x2y (nspw, nfreq),
+ * taper (nfreq), beam_sq_area (nspw, npol, nfreq); freq_power = 4 (Jy^2 Hz^2 power and the thermal
+ * estimate) or 0 (K^2 sr^2 Hz^2 power). */
+int sds_conversion_integral(const double *freq, const double *x2y, const double *taper,
+                            const double *beam_sq_area, int nspw, int npol, int nfreq,
+                            int freq_power, double *out, sds_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,17 @@ class EngineDesc(C.Structure):
     ]
 
 
+SDS_COSMO_MAX_NU = 4
+
+
+class CosmoParams(C.Structure):
+    _fields_ = [
+        ("h0_km_s_mpc", C.c_double), ("om0", C.c_double), ("ode0", C.c_double), ("ogamma0", C.c_double),
+        ("neff_per_nu", C.c_double), ("nmassless_nu", C.c_double), ("nu_y", C.c_double * SDS_COSMO_MAX_NU),
+        ("nmassive_nu", C.c_int32), ("has_massive_nu_or_radiation", C.c_int32),
+    ]
+
+
 _SIGNATURES = {
     "sds_last_error": (C.c_char_p, []),
     "sds_version": (_i32, []),
@@ -61,6 +72,8 @@ _SIGNATURES = {
                                     _vp, _vp, _vp]),
     "sds_bootstrap_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
     "sds_bootstrap_indices": (_i32, [_u64, _i64, _i64, _vp, _vp]),
+    "sds_cosmo_evaluate": (_i32, [C.POINTER(CosmoParams), _vp, _i64, _vp, _vp, _vp]),
+    "sds_conversion_integral": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -24,6 +24,11 @@ def _value(x):
     return x.value if is_quantity(x) else x
 
 
+def _default_cosmology():
+    from . import cosmo as simple_cosmo
+    return simple_cosmo.default_cosmology.get()
+
+
 class UVDataLite:
     """The slice of a pyuvdata UVData object ``add_uvdata`` reads (ds.py:903-932).
 
@@ -109,7 +114,7 @@ class DelaySpectrum:
         self.power_array = self.noise_power = self.thermal_power = None
         self.redshift = self.k_parallel = self.k_perpendicular = None
         self.unit_conversion = self.thermal_conversion = None
-        self.cosmology = None
+        self.cosmology = _default_cosmology()  # ds.py:551-558
         self.taper = windows.blackmanharris  # ds.py:541-549
 
         if uv is not None:
@@ -292,11 +297,13 @@ class DelaySpectrum:
     def from_arrays(cls, data_array, flag_array, nsample_array, freq_array, integration_time,
                     polarization_array, vis_units="Jy", lst_array=None, baseline_array=None,
                     ant_1_array=None, ant_2_array=None, trcvr=None, beam_area=None, taper=None,
-                    precision="complex128", noise_seed=0):
+                    precision="complex128", noise_seed=0, uvw=None):
         """Build from arrays already in the reference's 6-D layout
         (Nspws, Nuv, Npols, Nbls, Ntimes, Nfreqs) (ds.py:159-176); ``freq_array`` is
         (Nspws, Nfreqs) in Hz, ``integration_time`` (Nbls, Ntimes) in s."""
         self = cls(precision=precision, noise_seed=noise_seed)
+        if uvw is not None:  # baseline vector of the redundant group, metres (ds.py:984)
+            self.uvw = Quantity(np.asarray(_value(uvw), dtype=np.float64).reshape(3), "m")
         shape = tuple(data_array.shape)
         if len(shape) != 6:
             raise ValueError("data_array must be (Nspws, Nuv, Npols, Nbls, Ntimes, Nfreqs)")
@@ -335,7 +342,7 @@ class DelaySpectrum:
         baselines sorted by baseline number, times by unwrapped LST)."""
         if not isinstance(uv, UVDataLite):
             raise ValueError("Input data object must be an instance or subclass of UVData.")
-        red_groups = uv.get_redundancies(tol=tol, include_conjugates=True)[0]
+        red_groups, uvw_centers = uv.get_redundancies(tol=tol, include_conjugates=True)[:2]
         if len(red_groups) > 1:
             raise ValueError(
                 "A DelaySpectrum object can only perform a Fourier "
@@ -350,6 +357,7 @@ class DelaySpectrum:
                 "a new object to cross-multipy different "
                 "data."
             )
+        self.uvw = Quantity(np.asarray(uvw_centers[0], dtype=np.float64), "m")  # ds.py:984
         bls = uv.get_baseline_nums()  # sorted unique  (ds.py:931)
         P, B, T, F = uv.Npols, uv.Nbls, uv.Ntimes, uv.Nfreqs
         data = np.zeros((P, B, T, F), dtype=np.complex64)  # utils.py:38
@@ -568,8 +576,8 @@ class DelaySpectrum:
     # ------------------------------------------------------------------ power
     def calculate_delay_spectrum(self, run_check=True, run_check_acceptability=True,
                                  cosmology=None, littleh_units=False):
-        """ds.py:3585-3635.  Power stays in (data unit)^2 (the reference's
-        ``remove_cosmology`` state): astropy cosmology is not available."""
+        """ds.py:3585-3635: delay transform, cross multiplication, thermal estimate and, last,
+        ``update_cosmology`` (power in mK^2 Mpc^3; ``remove_cosmology()`` undoes it)."""
         if self.Nuv == 0:
             raise ValueError(
                 "No data has be loaded. Add UVData objects before "
@@ -581,7 +589,120 @@ class DelaySpectrum:
         unit = self._data_unit ** 2
         self.power_array = Quantity(ops.cross_power_full(self._data[:, 0], self._data[:, j]), unit)
         self.noise_power = Quantity(ops.cross_power_full(self._noise[:, 0], self._noise[:, j]), unit)
+        self.unit_conversion = self.thermal_conversion = None  # fresh arrays carry no conversion
         self.calculate_thermal_sensitivity()
+        self.update_cosmology(cosmology=cosmology, littleh_units=littleh_units)
+
+    # ------------------------------------------------------------------ cosmology
+    _LITTLEH_POWER = Unit("mK^2 Mpc^3 littleh^-3")
+
+    def _scale_sp(self, q, factor_sp, unit):
+        """q * factor[s, p] broadcast over the trailing axes, relabelled."""
+        v = q.value
+        f = torch.as_tensor(np.asarray(factor_sp, dtype=np.float64), device=v.device)
+        f = f.reshape(f.shape + (1,) * (v.dim() - 2))
+        return Quantity(v * f, unit)
+
+    def remove_cosmology(self):
+        """ds.py:1133-1199: take the cosmological conversion back out of the power estimates."""
+        if self.cosmology is None:
+            raise ValueError(f"Cannot remove cosmology of type {type(None)}")
+        self.k_parallel = None
+        self.k_perpendicular = None
+        h3 = (self.cosmology.H0 / 100.0) ** 3
+        if self.power_array is not None:
+            if self.power_array.unit == self._LITTLEH_POWER:
+                self.power_array = Quantity(self.power_array.value / h3, "mK^2 Mpc^3")
+                self.noise_power = Quantity(self.noise_power.value / h3, "mK^2 Mpc^3")
+            if self.unit_conversion is not None and not self.power_array.unit.is_equivalent(
+                    (Unit("Jy^2 Hz^2"), Unit("K^2 sr^2 Hz^2"))):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    inv = 1.0 / np.asarray(self.unit_conversion.value, dtype=np.float64)
+                unit = self.power_array.unit / self.unit_conversion.unit
+                self.power_array = self._scale_sp(self.power_array, inv, unit)
+                self.noise_power = self._scale_sp(self.noise_power, inv, unit)
+        if self.thermal_power is not None:
+            if self.thermal_power.unit == self._LITTLEH_POWER:
+                self.thermal_power = Quantity(self.thermal_power.value / h3, "mK^2 Mpc^3")
+            if self.thermal_conversion is not None and not self.thermal_power.unit.is_equivalent(
+                    (Unit("Jy^2 Hz^2"), Unit("K^2 sr^2 Hz^6"))):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    inv = 1.0 / np.asarray(self.thermal_conversion.value, dtype=np.float64)
+                self.thermal_power = self._scale_sp(self.thermal_power, inv,
+                                                    self.thermal_power.unit / self.thermal_conversion.unit)
+        self.unit_conversion = None
+        self.thermal_conversion = None
+
+    def _conversion_integral(self, x2y, freq_power):
+        """trapz_f(freq^pw / X2Y * taper^2 * beam_sq_area) per (window, pol), on the device."""
+        dev = self._device()
+        freq = torch.as_tensor(np.ascontiguousarray(self.freq_array.value, dtype=np.float64), device=dev)
+        x = torch.as_tensor(np.ascontiguousarray(x2y, dtype=np.float64), device=dev)
+        tap = torch.as_tensor(np.ascontiguousarray(self.taper(self.Nfreqs), dtype=np.float64), device=dev)
+        beam = torch.as_tensor(np.ascontiguousarray(_value(self.beam_sq_area), dtype=np.float64), device=dev)
+        out = torch.empty((self.Nspws, self.Npols), dtype=torch.float64, device=dev)
+        rc = ops._lib.load().sds_conversion_integral(ops.ptr(freq), ops.ptr(x), ops.ptr(tap), ops.ptr(beam),
+                                                     self.Nspws, self.Npols, self.Nfreqs, int(freq_power),
+                                                     ops.ptr(out), ops.stream_ptr())
+        ops.check(rc, "sds_conversion_integral")
+        return out.cpu().numpy()
+
+    def update_cosmology(self, cosmology=None, littleh_units=False):
+        """ds.py:1201-1365: redshift, k_parallel, k_perpendicular and the conversion of the power
+        estimates to mK^2 Mpc^3 (per (window, pol) integrals of nu^4 / X2Y * taper^2 * beam^2)."""
+        from . import cosmo as simple_cosmo
+
+        self.remove_cosmology()
+        if cosmology is not None:
+            if not isinstance(cosmology, simple_cosmo.FlatLambdaCDM):
+                raise ValueError("Input cosmology must a sub-class of astropy.cosmology.core.Cosmology")
+            self.cosmology = cosmology
+        else:
+            self.cosmology = simple_cosmo.default_cosmology.get()
+        freq = np.asarray(self.freq_array.value, dtype=np.float64)
+        self.redshift = simple_cosmo.calc_z(self.freq_array).mean(axis=1)
+        delay_s = np.asarray(self.delay_array.value, dtype=np.float64) * 1e-9
+        self.k_parallel = simple_cosmo.eta2kparr(Quantity(delay_s.reshape(1, self.Ndelays), "s"),
+                                                 self.redshift.reshape(self.Nspws, 1), cosmo=self.cosmology)
+        if self.uvw is not None:
+            uvw_wave = np.linalg.norm(np.asarray(_value(self.uvw), dtype=np.float64)) / (
+                simple_cosmo.C_M_S / freq.mean(axis=1))
+            self.k_perpendicular = simple_cosmo.u2kperp(uvw_wave, self.redshift, cosmo=self.cosmology)
+        x2y = i4 = None
+        if self.power_array is not None or self.thermal_power is not None:
+            x2y = simple_cosmo.X2Y(simple_cosmo.calc_z(self.freq_array), cosmo=self.cosmology).value
+            with np.errstate(divide="ignore", invalid="ignore"):
+                i4 = self._conversion_integral(x2y, 4)
+        if self.power_array is not None:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if self.power_array.unit == Unit("Jy^2 Hz^2"):
+                    # (c^2 sr / 2 k_B)^2 / integral, SI -> mK^2 Mpc^3 / (Jy^2 Hz^2): K^2 -> mK^2, J -> 1e26 Jy m^2
+                    conv = (simple_cosmo.C_M_S**2 / (2 * simple_cosmo.K_B)) ** 2 / i4 * 1e6 * 1e-52
+                    self.unit_conversion = Quantity(conv, "mK^2 Mpc^3 Jy^-2 Hz^-2")
+                elif self.power_array.unit == Unit("K^2 sr^2 Hz^2"):
+                    conv = 1.0 / self._conversion_integral(x2y, 0) * 1e6
+                    self.unit_conversion = Quantity(conv, "mK^2 Mpc^3 K^-2 sr^-2 Hz^-2")
+                else:
+                    self.unit_conversion = Quantity(np.ones((self.Nspws, self.Npols)), "")
+            unit = self.power_array.unit * self.unit_conversion.unit
+            if not self._data_unit == Unit("Hz"):
+                unit = Unit("mK^2 Mpc^3")
+            self.power_array = self._scale_sp(self.power_array, self.unit_conversion.value, unit)
+            self.noise_power = self._scale_sp(self.noise_power, self.unit_conversion.value, unit)
+        if self.thermal_power is not None:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                self.thermal_conversion = Quantity(1.0 / i4 * 1e6, "mK^2 Mpc^3 K^-2 sr^-2 Hz^-6")
+            self.thermal_power = self._scale_sp(self.thermal_power, self.thermal_conversion.value, "mK^2 Mpc^3")
+        if littleh_units:
+            h = self.cosmology.H0 / 100.0
+            self.k_parallel = Quantity(self.k_parallel.value / h, "littleh Mpc^-1")
+            if self.k_perpendicular is not None:
+                self.k_perpendicular = Quantity(self.k_perpendicular.value / h, "littleh Mpc^-1")
+            if self.power_array is not None:
+                self.power_array = Quantity(self.power_array.value * h**3, self._LITTLEH_POWER)
+                self.noise_power = Quantity(self.noise_power.value * h**3, self._LITTLEH_POWER)
+            if self.thermal_power is not None:
+                self.thermal_power = Quantity(self.thermal_power.value * h**3, self._LITTLEH_POWER)
 
     def _thermal_inputs(self):
         freq = self.freq_array.value

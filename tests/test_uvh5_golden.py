@@ -132,6 +132,7 @@ def test_bundled_files_through_delay_spectrum(cuda_device, name, wins, precision
     g_re, g_im = rng.standard_normal(ds.data_array.shape), rng.standard_normal(ds.data_array.shape)
     ds.generate_noise(normals=(g_re, g_im))
     ds.calculate_delay_spectrum()
+    ds.remove_cosmology()  # t_ds.py:1122-1147 compares the raw products
 
     state = orc.select_spectral_windows(dict(
         data_array=ex["vis"], noise_array=np.zeros_like(ex["vis"]), nsample_array=ex["nsample"],
