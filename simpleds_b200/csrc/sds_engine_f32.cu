@@ -6,8 +6,9 @@
 // version showed (profiles/r1_*): the kernel is bound by instruction issue and by
 // the FMA pipe, not by DRAM -- so the arithmetic is packed fp32x2 (sds_packed.cuh:
 // one FADD2 per complex add, two FFMA2-class instructions per complex multiply,
-// "* -i" as an operand modifier) and the accumulators are slimmed to fit three
-// CTAs per SM.
+// "* -i" as an operand modifier), the accumulators are slimmed to fit three CTAs per SM,
+// the exchange addresses cost one LOP3 per access (TeamFftX), and whatever the noise and thermal
+// legs both need (nsample^-1/2, the flag select) is computed once.  DESIGN.md sections 3.1 / 4.
 #include "sds_engine.cuh"
 #include "sds_packed.cuh"
 
@@ -263,7 +264,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       // ---- data leg: (1 - flag) * taper * delta_f ; noise leg: draw * sigma(nsample, t_int) --
       f2 vd[8], vn[8];
       // mask = (1 - flag) (ds.py:3503-3505); taper and delta_f ride on the same multiplier
-      // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
+      // (utils.py:552-560): m = mask * tapdf for the data, m * sigc (sigma coefficient) for the noise
       if (HAS_N && P.noise_mode == 1) {
         float rad[8], cs[8], sn[8];
         engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
