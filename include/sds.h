@@ -238,6 +238,15 @@ int sds_bootstrap_gather(const void *in, const int64_t *index, int elem_bytes, i
 int sds_bootstrap_indices(uint64_t seed, int64_t n, int64_t nboot, int64_t *index,
                           sds_stream stream);
 
+/* ---- ingest: SURVEY 8(f2) -------------------------------------------------------------------
+ * utils.py:15-168 (get_data_array / get_nsample_array / get_flag_array: one np.transpose per
+ * baseline) with the ordering rules of delay_spectrum.py:913-973 (baselines by baseline number,
+ * times by unwrapped LST) folded into ONE row permutation computed by the caller:
+ *   out[p][r][f] = in[perm[r]][f][p],   in (nblt, nfreq, npol), out (npol, nrow, nfreq),
+ * elem_bytes 1 (flags), 4 (nsample), 8 (complex64 visibilities) or 16.  Bit-exact (a copy). */
+int sds_ingest_gather(const void *in, const int64_t *perm, int elem_bytes, int64_t nblt,
+                      int64_t nrow, int nfreq, int npol, void *out, sds_stream stream);
+
 /* ---- cosmological normalisation: SURVEY 8(f1) ---------------------------------------------
  * The flat-LambdaCDM background the reference gets from astropy (cosmo.py:20: Planck15), as plain
  * numbers: Ode0 = 1 - Om0 - Ogamma0 - Onu0 already evaluated by the caller. */

@@ -72,6 +72,7 @@ _SIGNATURES = {
                                     _vp, _vp, _vp]),
     "sds_bootstrap_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
     "sds_bootstrap_indices": (_i32, [_u64, _i64, _i64, _vp, _vp]),
+    "sds_ingest_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _i32, _i32, _vp, _vp]),
     "sds_cosmo_evaluate": (_i32, [C.POINTER(CosmoParams), _vp, _i64, _vp, _vp, _vp]),
     "sds_conversion_integral": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
 }

@@ -357,30 +357,37 @@ class DelaySpectrum:
                 "a new object to cross-multipy different "
                 "data."
             )
-        self.uvw = Quantity(np.asarray(uvw_centers[0], dtype=np.float64), "m")  # ds.py:984
         bls = uv.get_baseline_nums()  # sorted unique  (ds.py:931)
         P, B, T, F = uv.Npols, uv.Nbls, uv.Ntimes, uv.Nfreqs
-        data = np.zeros((P, B, T, F), dtype=np.complex64)  # utils.py:38
-        nsamp = np.zeros((P, B, T, F), dtype=np.float32)  # utils.py:78
-        flag = np.zeros((P, B, T, F), dtype=bool)
-        itime = np.zeros((B, T), dtype=np.float32)  # utils.py:157
+        # utils.py:15-168 (get_data_array / get_nsample_array / get_flag_array /
+        # get_integration_time) + the LST sort of ds.py:913-916 as ONE row permutation:
+        # output row (baseline c, time t) <- baseline-time row perm[c, t] of the UVData arrays;
+        # the (Nblts, Nfreqs, Npols) -> (Npols, Nbls, Ntimes, Nfreqs) gather runs on the device
+        lst = uv.lst_array[uv.baseline_array == uv.baseline_array[0]]  # ds.py:913-915
+        lst_inds = np.argsort(np.unwrap(lst))  # ds.py:916
+        perm = np.zeros((B, T), dtype=np.int64)
         ant1 = np.zeros(B, dtype=np.int64)
         ant2 = np.zeros(B, dtype=np.int64)
         for c, b in enumerate(bls):
             inds = np.nonzero(uv.baseline_array == b)[0]
-            data[:, c] = np.transpose(uv.data_array[inds], [2, 0, 1])
-            nsamp[:, c] = np.transpose(uv.nsample_array[inds], [2, 0, 1])
-            flag[:, c] = np.transpose(uv.flag_array[inds], [2, 0, 1])
-            itime[c] = uv.integration_time[inds]
+            perm[c] = inds[lst_inds]
             ant1[c], ant2[c] = uv.ant_1_array[inds[0]], uv.ant_2_array[inds[0]]
-        lst = uv.lst_array[uv.baseline_array == uv.baseline_array[0]]  # ds.py:913-915
-        lst_inds = np.argsort(np.unwrap(lst))  # ds.py:916
+        itime = np.asarray(uv.integration_time, dtype=np.float32)[perm]  # utils.py:157
+        dev = self._device()
+        perm_d = torch.as_tensor(perm.reshape(-1), device=dev)
+
+        def gather(arr, dtype):  # -> (1, 1, Npols, Nbls, Ntimes, Nfreqs)
+            t = torch.as_tensor(np.ascontiguousarray(arr), device=dev).to(dtype).reshape(-1, F, P)
+            return ops.ingest_gather(t, perm_d).reshape(1, 1, P, B, T, F)
+
         this = DelaySpectrum.from_arrays(
-            data[None, None][..., lst_inds, :], flag[None, None][..., lst_inds, :],
-            nsamp[None, None][..., lst_inds, :].astype(np.float64), uv.freq_array[None],
-            itime[:, lst_inds].astype(np.float64), uv.polarization_array, vis_units=uv.vis_units,
+            gather(uv.data_array, torch.complex64),  # utils.py:38
+            gather(uv.flag_array, torch.bool),
+            gather(uv.nsample_array, torch.float32).to(torch.float64),  # utils.py:78
+            uv.freq_array[None], itime.astype(np.float64), uv.polarization_array, vis_units=uv.vis_units,
             lst_array=np.unwrap(lst)[lst_inds], baseline_array=bls, ant_1_array=ant1,
             ant_2_array=ant2, precision=self.precision, noise_seed=self.noise_seed,
+            uvw=np.asarray(uvw_centers[0], dtype=np.float64),  # ds.py:984
         )
         this.Nants_data, this.Nants_telescope = uv.Nants_data, uv.Nants_telescope
         this.x_orientation = uv.x_orientation

@@ -336,3 +336,16 @@ def bootstrap_gather(x, index, axis):
                                           inner, _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "sds_bootstrap_gather")
     return out
+
+
+# ---- ingest -----------------------------------------------------------------
+def ingest_gather(x, perm):
+    """x: (Nblts, Nfreqs, Npols) CUDA tensor of 1-, 4-, 8- or 16-byte elements; perm: int64 (R,)
+    CUDA tensor of baseline-time rows.  Returns (Npols, R, Nfreqs): out[p, r, f] = x[perm[r], f, p]."""
+    x, perm = x.contiguous(), perm.contiguous()
+    nblt, nfreq, npol = (int(v) for v in x.shape)
+    out = torch.empty((npol, perm.numel(), nfreq), dtype=x.dtype, device=x.device)
+    rc = _lib.load().sds_ingest_gather(ptr(x), ptr(perm), x.element_size(), nblt, perm.numel(), nfreq, npol,
+                                       ptr(out), stream_ptr())
+    check(rc, "sds_ingest_gather")
+    return out

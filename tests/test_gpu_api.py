@@ -383,3 +383,33 @@ def test_spectrum_on_no_data_and_twice(cuda_device):
     assert ds.data_type == "delay"
     assert np.array_equal(ds.power_array.numpy(), first)
     assert np.array_equal(ds.thermal_power.numpy(), thermal)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,F,dtype", [(1, 21, np.complex64), (2, 203, np.complex64), (4, 5, np.float32),
+                                        (4, 1024, np.complex64), (2, 64, np.uint8), (3, 17, np.complex128)])
+def test_ingest_gather_is_the_per_baseline_transpose(cuda_device, P, F, dtype):
+    """utils.py:15-168: data[:, c] = transpose(uv.data_array[inds], [2, 0, 1]) per baseline, with the
+    LST sort of ds.py:913-916 -- one device gather, bit-exact."""
+    import torch
+
+    from simpleds_b200 import ops
+    rng = np.random.default_rng(P * 1000 + F)
+    B, T = 7, 5
+    nblt = B * T
+    if np.issubdtype(dtype, np.complexfloating):
+        x = (rng.standard_normal((nblt, F, P)) + 1j * rng.standard_normal((nblt, F, P))).astype(dtype)
+    elif dtype == np.uint8:
+        x = rng.integers(0, 2, (nblt, F, P)).astype(np.uint8)
+    else:
+        x = rng.standard_normal((nblt, F, P)).astype(dtype)
+    bl = np.tile(rng.permutation(B), T)                       # time-major blt axis, shuffled baselines
+    lst_inds = rng.permutation(T)
+    want = np.zeros((P, B, T, F), dtype=dtype)
+    perm = np.zeros((B, T), dtype=np.int64)
+    for c in range(B):
+        inds = np.nonzero(bl == c)[0]
+        want[:, c] = np.transpose(x[inds], [2, 0, 1])[:, lst_inds]
+        perm[c] = inds[lst_inds]
+    got = ops.ingest_gather(torch.as_tensor(x, device="cuda"), torch.as_tensor(perm.reshape(-1), device="cuda"))
+    assert np.array_equal(got.cpu().numpy().reshape(P, B, T, F), want)
