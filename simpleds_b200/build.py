@@ -37,15 +37,18 @@ def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     flags = list(NVCC_FLAGS) + os.environ.get("SDS_NVCC_FLAGS", "").split()
-    objs = []
-    for src in SOURCES:
+    objs, procs = [], []
+    for src in SOURCES:  # one nvcc per translation unit, all at once (the engines take ~20 s each)
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     cmd = [_nvcc(), *flags, "-shared", "-o", LIB, *objs]
     subprocess.run(cmd, check=True)
     return LIB
