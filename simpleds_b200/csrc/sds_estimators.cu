@@ -26,7 +26,20 @@ __global__ void wavg_inner_kernel(const double *__restrict__ x, const double *__
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t o = e / inner, i = e % inner;
     WavgAcc a = {0.0, 0.0, 0.0};
-    for (int64_t k = 0; k < n; ++k) {
+    int64_t k = 0;
+    for (; k + 4 <= n; k += 4) {  // four independent loads in flight per array
+      double xs[4], ss[4], ws[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t idx = (o * n + k + u) * inner + i;
+        xs[u] = x[idx];
+        ss[u] = sig[idx];
+        ws[u] = w ? (w1d ? w[k + u] : w[idx]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wavg_add(a, xs[u], ss[u], w ? ws[u] : 1.0 / (ss[u] * ss[u]));
+    }
+    for (; k < n; ++k) {
       const int64_t idx = (o * n + k) * inner + i;
       const double s = sig[idx];
       const double wk = w ? (w1d ? w[k] : w[idx]) : 1.0 / (s * s);
@@ -45,7 +58,20 @@ __global__ void wavg_last_kernel(const double *__restrict__ x, const double *__r
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t o = warp; o < outer; o += nwarp) {
     WavgAcc a = {0.0, 0.0, 0.0};
-    for (int64_t k = lane; k < n; k += 32) {
+    int64_t k = lane;
+    for (; k + 96 < n; k += 128) {  // four independent loads in flight per array
+      double xs[4], ss[4], ws[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t idx = o * n + k + 32 * u;
+        xs[u] = x[idx];
+        ss[u] = sig[idx];
+        ws[u] = w ? (w1d ? w[k + 32 * u] : w[idx]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wavg_add(a, xs[u], ss[u], w ? ws[u] : 1.0 / (ss[u] * ss[u]));
+    }
+    for (; k < n; k += 32) {
       const int64_t idx = o * n + k;
       const double s = sig[idx];
       const double wk = w ? (w1d ? w[k] : w[idx]) : 1.0 / (s * s);
@@ -119,7 +145,7 @@ __global__ void boot_index_kernel(uint32_t k0, uint32_t k1, int64_t n, int64_t c
 
 static int grid_for(int64_t work, int block) {
   int64_t g = (work + block - 1) / block;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = 148 * 32;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
