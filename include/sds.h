@@ -97,6 +97,19 @@ int sds_generate_noise(const double *sigma, int64_t n, const double *g_re,
                        const double *g_im, uint64_t seed, uint64_t offset, void *out,
                        int out_dtype, sds_stream stream);
 
+/* The noise leg of the unfused API in one call: sds_noise_sigma -> sds_generate_noise ->
+ * sds_delay_transform (forward, flag mask applied) enqueued back to back -- ds.py:3544-3583,
+ * utils.py:486-506 and the noise half of ds.py:3503-3517.  Arrays are the 6-D
+ * (S,U,P,B,T,F) layout with F == the plan's nfreq; `sigma_scratch` fp64 and `noise_freq`
+ * (the frequency-domain realisation the reference keeps as noise_array) are caller-provided,
+ * `noise_delay` receives the transformed noise; `dtype` SDS_C64 (SDS_F32 plan) or SDS_C128
+ * (SDS_F64 plan) for both complex arrays.  g_re / g_im / seed / offset as in sds_generate_noise. */
+int sds_noise_transform(const sds_plan *plan, const double *coef, const double *int_time,
+                        const void *nsample, int nsample_dtype, int S, int U, int P, int B, int T,
+                        int F, const uint8_t *flags, double delta_f, uint64_t seed, uint64_t offset,
+                        const double *g_re, const double *g_im, double *sigma_scratch,
+                        void *noise_freq, void *noise_delay, int dtype, sds_stream stream);
+
 /* Materialised cross power, utils.py:387-389 as called at ds.py:3620-3633:
  * out[s,p,i,j,t,d] = a2[s,p,i,t,d] * conj(a1[s,p,j,t,d]).  a1/a2 have element
  * strides (stride_s, stride_p) over their first two axes and are contiguous in

@@ -57,6 +57,8 @@ _SIGNATURES = {
                                    C.POINTER(C.c_int32), _dbl, _i32, _vp, _i32, _vp]),
     "sds_noise_sigma": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "sds_generate_noise": (_i32, [_vp, _i64, _vp, _vp, _u64, _u64, _vp, _i32, _vp]),
+    "sds_noise_transform": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _dbl,
+                                   _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "sds_cross_power_full": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp]),
     "sds_thermal_power_full": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
                                       _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -169,3 +169,27 @@ extern "C" int sds_plan_destroy(sds_plan *plan) {
 
 extern "C" int sds_plan_nfreq(const sds_plan *plan) { return plan ? plan->p.nfreq : SDS_EINVAL; }
 extern "C" int sds_plan_math(const sds_plan *plan) { return plan ? plan->p.math : SDS_EINVAL; }
+
+// ---- noise leg of the unfused API in one call ---------------------------
+// sigma (ds.py:3544-3583) -> realisation (utils.py:486-506) -> delay transform with the flag
+// mask (ds.py:3503-3517, utils.py:509-566): the three kernels above enqueued back to back on
+// `stream`; nothing is allocated (the caller passes the sigma scratch and receives the
+// frequency-domain realisation, which the reference keeps as noise_array until delay_transform).
+extern "C" int sds_noise_transform(const sds_plan *plan, const double *coef, const double *int_time,
+                                   const void *nsample, int nsample_dtype, int S, int U, int P, int B,
+                                   int T, int F, const uint8_t *flags, double delta_f, uint64_t seed,
+                                   uint64_t offset, const double *g_re, const double *g_im,
+                                   double *sigma_scratch, void *noise_freq, void *noise_delay,
+                                   int dtype, sds_stream stream) {
+  SDS_CHECK_ARG(plan && sigma_scratch && noise_freq && noise_delay, "sds_noise_transform: NULL pointer");
+  SDS_CHECK_ARG(F == plan->p.nfreq, "sds_noise_transform: nfreq %d does not match the plan (%d)", F,
+                plan->p.nfreq);
+  const int64_t rows = (int64_t)S * U * P * B * T;
+  int rc = sds_noise_sigma(coef, int_time, nsample, nsample_dtype, S, U, P, B, T, F, sigma_scratch, stream);
+  if (rc != SDS_OK) return rc;
+  rc = sds_generate_noise(sigma_scratch, rows * F, g_re, g_im, seed, offset, noise_freq, dtype, stream);
+  if (rc != SDS_OK) return rc;
+  const int32_t start = 0;
+  return sds_delay_transform(plan, noise_freq, dtype, F, flags, F, rows, 1, &start, delta_f, 0,
+                             noise_delay, dtype, stream);
+}

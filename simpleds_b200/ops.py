@@ -134,6 +134,33 @@ def generate_noise(sigma, seed=0, offset=0, normals=None, out_dtype=torch.comple
     return out
 
 
+def noise_transform(plan, coef, int_time, nsample, flags, delta_f, seed=0, offset=0, normals=None,
+                    out_dtype=torch.complex128):
+    """sigma -> realisation -> delay transform in one C call (sds_noise_transform).
+    Returns (noise_freq, noise_delay), both with nsample's 6-D shape."""
+    _lib.require_cuda()
+    S, U, P, B, T, F = nsample.shape
+    n = nsample.contiguous()
+    coef = coef.to(torch.float64).contiguous()
+    it = int_time.to(torch.float64).contiguous()
+    fl = None if flags is None else flags.contiguous().view(torch.uint8)
+    sig = torch.empty(n.shape, dtype=torch.float64, device=n.device)
+    nf = torch.empty(n.shape, dtype=out_dtype, device=n.device)
+    nd = torch.empty_like(nf)
+    g_re = g_im = None
+    if normals is not None:
+        g_re = torch.as_tensor(normals[0], dtype=torch.float64, device=n.device).contiguous()
+        g_im = torch.as_tensor(normals[1], dtype=torch.float64, device=n.device).contiguous()
+    check(
+        _lib.load().sds_noise_transform(plan.handle, ptr(coef), ptr(it), ptr(n), real_dtype_code(n), S, U, P,
+                                        B, T, F, ptr(fl), float(delta_f), int(seed), int(offset), ptr(g_re),
+                                        ptr(g_im), ptr(sig), ptr(nf), ptr(nd), complex_dtype_code(nf),
+                                        stream_ptr()),
+        "sds_noise_transform",
+    )
+    return nf, nd
+
+
 def _sp_strides(a):
     """(S,P,B,T,D) view, possibly strided over S and P but contiguous in (B,T,D)."""
     S, P, B, T, D = a.shape

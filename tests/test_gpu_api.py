@@ -413,3 +413,30 @@ def test_ingest_gather_is_the_per_baseline_transpose(cuda_device, P, F, dtype):
         perm[c] = inds[lst_inds]
     got = ops.ingest_gather(torch.as_tensor(x, device="cuda"), torch.as_tensor(perm.reshape(-1), device="cuda"))
     assert np.array_equal(got.cpu().numpy().reshape(P, B, T, F), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_noise_transform_is_the_chain_of_the_three_calls(cuda_device, precision):
+    """sds_noise_transform == sds_noise_sigma -> sds_generate_noise ->
+    sds_delay_transform, bit for bit, with injected normals and with the Philox stream."""
+    import torch
+    from scipy.signal import windows
+
+    from simpleds_b200 import ops
+    from simpleds_b200._lib import SDS_F32, SDS_F64
+    rng = np.random.default_rng(77)
+    S, U, P, B, T, F = 2, 1, 2, 3, 4, 32
+    cdt = torch.complex128 if precision == "complex128" else torch.complex64
+    plan = ops.get_plan(F, SDS_F64 if precision == "complex128" else SDS_F32, windows.blackmanharris)
+    coef = torch.as_tensor(rng.uniform(1.0, 2.0, (S, P, F)), device="cuda")
+    it = torch.as_tensor(rng.uniform(5.0, 10.0, (B, T)), device="cuda")
+    ns = torch.as_tensor(rng.integers(0, 50, (S, U, P, B, T, F)).astype(np.float64), device="cuda")
+    fl = torch.as_tensor(rng.random((S, U, P, B, T, F)) < 0.1, device="cuda")
+    g = (rng.standard_normal(ns.shape), rng.standard_normal(ns.shape))
+    for normals in (g, None):
+        nf, nd = ops.noise_transform(plan, coef, it, ns, fl, 97656.25, seed=5, normals=normals, out_dtype=cdt)
+        sig = ops.noise_sigma(coef, it, ns)
+        want_f = ops.generate_noise(sig, seed=5, normals=normals, out_dtype=cdt)
+        want_d = ops.delay_transform(plan, want_f.reshape(-1, F), fl.reshape(-1, F), 97656.25)
+        assert torch.equal(nf, want_f) and torch.equal(nd.reshape(-1), want_d.reshape(-1))
