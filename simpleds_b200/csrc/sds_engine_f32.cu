@@ -178,17 +178,17 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       --pleft;
     };
 
-    // noise multiplier per channel on top of the data's mask * taper * delta_f: sigma coefficient
-    // * sqrt(ln 2) (non-finite sigma -> 0, ds.py:3575-3582); 1 for injected noise
+    // noise multiplier per channel: sigma coefficient * sqrt(ln 2) * taper * delta_f (non-finite
+    // sigma -> 0, ds.py:3575-3582); taper * delta_f alone for injected noise
     float sigc[8];
     if (HAS_N) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (P.noise_mode == 1) {
           const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
-          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 : 0.f;
+          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * tapdf[r] : 0.f;
         } else {
-          sigc[r] = 1.f;
+          sigc[r] = tapdf[r];
         }
       }
     }
@@ -264,26 +264,28 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       // ---- data leg: (1 - flag) * taper * delta_f ; noise leg: draw * sigma(nsample, t_int) --
       f2 vd[8], vn[8];
       // mask = (1 - flag) (ds.py:3503-3505); taper and delta_f ride on the same multiplier
-      // (utils.py:552-560): m = mask * tapdf for the data, m * sigc (sigma coefficient) for the noise
+      // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
       if (HAS_N && P.noise_mode == 1) {
         float rad[8], cs[8], sn[8];
         engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float m = (active && fl_s[TPR * r] == 0) ? tapdf[r] : 0.f;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, m);
-          // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581)
-          const float amp = (m * (sigc[r] * rt)) * (rad[r] * av[r]);
+          const bool k = active && fl_s[TPR * r] == 0;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          // sigma sqrt(-ln u1) = coef sqrt(-ln u1) / sqrt(t_int nsample)   (ds.py:3546-3581); the two
+          // selects run on the ALU pipe, the three products on the (binding) FP32 pipe
+          const float amp = ((k ? sigc[r] : 0.f) * rt) * (rad[r] * av[r]);
           vn[r] = f2_scale(f2_make(cs[r], sn[r]), amp);
         }
       } else {
         const int64_t e = e00 + (int64_t)(ct - t0) * P.nchan + (int64_t)ia * row_stride;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float m = (active && fl_s[TPR * r] == 0) ? tapdf[r] : 0.f;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, m);
+          const bool k = active && fl_s[TPR * r] == 0;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           if (HAS_N) {  // injected freq-domain noise (parity mode): plain loads
             const float2 c = active ? P.noise_in[e + tau + TPR * r] : make_float2(0.f, 0.f);
+            const float m = k ? sigc[r] : 0.f;
             vn[r] = f2_make(c.x * m, c.y * m);
           }
         }
