@@ -98,13 +98,18 @@ template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr int TWF_BYTES =
       ((LEGS & LEG_NOISE) && !(SAME && (LEGS & LEG_DATA))) ? fft_tw_total(N) * (int)sizeof(cpx<float>) : 0;
   static constexpr int TAB_BYTES = ((TW_BYTES + TWF_BYTES + 127) / 128) * 128;
-  // per worker: barriers (64 B) | ENG_STAGES slots | 2 exchange buffers per row
-  static constexpr int WORKER_BYTES = 64 + ENG_STAGES * SLOT + 2 * ROWS * BUF;
+  // per worker: barriers (64 B) | ENG_STAGES slots | 2 exchange buffers per row |
+  // thermal leg: 6 values per thread (first-channel sums of its two runs, for the left neighbour)
+  static constexpr int NB_BYTES = (LEGS & LEG_THERMAL) ? 6 * WORKER * (int)sizeof(T) : 0;
+  // the thermal leg transforms nothing: no exchange buffers, and a register budget for 16 warps / SM
+  static constexpr int XB_BYTES = (LEGS & (LEG_DATA | LEG_NOISE)) ? 2 * ROWS * BUF : 0;
+  static constexpr int MINB = (LEGS == LEG_THERMAL) ? (512 / THREADS < 1 ? 1 : 512 / THREADS) : ENG_MINBLOCKS;
+  static constexpr int WORKER_BYTES = 64 + ENG_STAGES * SLOT + XB_BYTES + NB_BYTES;
   static constexpr int SMEM = TAB_BYTES + NWORKER * WORKER_BYTES;
 };
 
 template <typename T, int N, int LEGS>
-__global__ void __launch_bounds__(EngCfg<T, N, LEGS>::THREADS, ENG_MINBLOCKS)
+__global__ void __launch_bounds__(EngCfg<T, N, LEGS>::THREADS, EngCfg<T, N, LEGS>::MINB)
 engine_kernel(const __grid_constant__ EngineParams P) {
   using C = EngCfg<T, N, LEGS>;
   constexpr int TPR = C::TPR, WORKER = C::WORKER, ROWS = C::ROWS;
@@ -128,6 +133,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   unsigned char *stages = wbase + 64;
   cpx<T> *bufA = reinterpret_cast<cpx<T> *>(stages + ENG_STAGES * C::SLOT + (size_t)sub * 2 * C::BUF);
   cpx<T> *bufB = reinterpret_cast<cpx<T> *>(reinterpret_cast<unsigned char *>(bufA) + C::BUF);
+  T *nb_s = reinterpret_cast<T *>(stages + ENG_STAGES * C::SLOT + C::XB_BYTES);
   if (wl == 0) {
     for (int i = 0; i < ENG_STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -218,13 +224,19 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     T S2[8], Pw[8];
     cpx<float> Sn1[8];
     float Sn2[8], Pn[8];
-    T tA[8], tAp[8], tB[8], tBp[8], tC[8], tCp[8];
+    // thermal sums per channel (c = 4 tau + 4 TPR h + j, q = 4 h + j): A = sum a, B = sum a / t_int,
+    // C = sum a^2 / t_int, a = nsample^-1/2 (0 where invalid).  Rows with a valid sample next to an
+    // invalid one additionally book what the panel mask (masked_invalid, ds.py:3697) removes into
+    // dfc[] (local memory, rare): per panel q, [0..2] left-end and [3..5] right-end deficits.
+    T tA[8], tB[8], tC[8];
+    T dfc[48];
+    bool dirty_time = false;
     double th_all_acc = 0.0, th_auto_acc = 0.0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       S1[r] = {(T)0, (T)0}; S2[r] = (T)0; Pw[r] = (T)0;
       Sn1[r] = {0.f, 0.f}; Sn2[r] = 0.f; Pn[r] = 0.f;
-      tA[r] = tAp[r] = tB[r] = tBp[r] = tC[r] = tCp[r] = (T)0;
+      tA[r] = tB[r] = tC[r] = (T)0;
     }
 
     // ---- consumer state ------------------------------------------------------------
@@ -308,23 +320,42 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         // thermal sums use their own channel map: two runs of 4 consecutive channels
         // per thread (c = 4 tau + 4 TPR h + j) -> two 128-bit loads + the right neighbours
         const T it = (tint > 0.f) ? (T)1 / (T)tint : (T)0;
+        bool dirty = false;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = 4 * tau + 4 * TPR * h;
           const float4 nv = *reinterpret_cast<const float4 *>(ns_s + c0);
-          const float nx = (c0 + 4 < N) ? ns_s[c0 + 4] : 0.f;  // no panel right of channel N-1
-          const float n5[5] = {nv.x, nv.y, nv.z, nv.w, nx};
-          T a5[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) a5[j] = (active && n5[j] > 0.f) ? rsqrt_t<T>(n5[j]) : (T)0;
+          const float n4[4] = {nv.x, nv.y, nv.z, nv.w};
+          bool ok[5];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const bool e = a5[j] > (T)0 && a5[j + 1] > (T)0;  // both ends of the panel valid
-            const T a0 = e ? a5[j] : (T)0, a1 = e ? a5[j + 1] : (T)0;
-            const int q = 4 * h + j;
-            tA[q] += a0; tAp[q] += a1;
-            tB[q] += a0 * it; tBp[q] += a1 * it;
-            tC[q] += a0 * a0 * it; tCp[q] += a1 * a1 * it;
+            ok[j] = active && n4[j] > 0.f;
+            const T a = ok[j] ? rsqrt_t<T>(n4[j]) : (T)0;
+            const T ai = a * it;
+            tA[4 * h + j] += a;
+            tB[4 * h + j] += ai;
+            tC[4 * h + j] += a * ai;
+          }
+          ok[4] = (c0 + 4 < N) ? (active && ns_s[c0 + 4] > 0.f) : ok[3];  // no panel right of N - 1
+          dirty |= (ok[0] != ok[1]) | (ok[1] != ok[2]) | (ok[2] != ok[3]) | (ok[3] != ok[4]);
+        }
+        if (dirty) {
+          if (!dirty_time) {
+#pragma unroll 1
+            for (int k = 0; k < 48; ++k) dfc[k] = (T)0;
+            dirty_time = true;
+          }
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
+            if (c + 1 >= N) continue;
+            const float nl = ns_s[c], nr = ns_s[c + 1];
+            if ((nl > 0.f) == (nr > 0.f)) continue;
+            const T a1 = rsqrt_t<T>(nl > 0.f ? nl : nr);
+            T *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
+            d[0] += a1;
+            d[1] += a1 * it;
+            d[2] += a1 * a1 * it;
           }
         }
       }
@@ -367,22 +398,48 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         if (HAS_T) {
           const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N;
           const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N;
+          // the right end of a run's last panel is the first channel of the next thread's run
+          T *mine = nb_s + ((sub * 2) * TPR + tau) * 3;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            T a = tA[q], ap = tAp[q], b = tB[q], bp = tBp[q];
-#pragma unroll
-            for (int off = TPR; off < 32; off <<= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, off);
-              ap += __shfl_xor_sync(0xffffffffu, ap, off);
-              b += __shfl_xor_sync(0xffffffffu, b, off);
-              bp += __shfl_xor_sync(0xffffffffu, bp, off);
-            }
-            const int c = 4 * tau + 4 * TPR * (q >> 2) + (q & 3);
-            const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
-            if (sub == 0) th_all_acc += l * (double)a * (double)b + rr * (double)ap * (double)bp;
-            th_auto_acc += l * (double)tC[q] + rr * (double)tCp[q];
-            tA[q] = tAp[q] = tB[q] = tBp[q] = tC[q] = tCp[q] = (T)0;
+          for (int h = 0; h < 2; ++h) {
+            mine[h * TPR * 3 + 0] = tA[4 * h];
+            mine[h * TPR * 3 + 1] = tB[4 * h];
+            mine[h * TPR * 3 + 2] = tC[4 * h];
           }
+          team_sync<WORKER>(bar_id);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            T nxt[3] = {(T)0, (T)0, (T)0};
+            if (tau + 1 < TPR || h == 0) {
+              const T *src = (tau + 1 < TPR) ? mine + h * TPR * 3 + 3 : nb_s + ((sub * 2 + 1) * TPR) * 3;
+              nxt[0] = src[0]; nxt[1] = src[1]; nxt[2] = src[2];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = 4 * h + j;
+              T a = tA[q], b = tB[q], cc = tC[q];
+              T ap = j < 3 ? tA[q + 1] : nxt[0], bp = j < 3 ? tB[q + 1] : nxt[1], cp = j < 3 ? tC[q + 1] : nxt[2];
+              if (dirty_time) {
+                a -= dfc[6 * q + 0]; b -= dfc[6 * q + 1]; cc -= dfc[6 * q + 2];
+                ap -= dfc[6 * q + 3]; bp -= dfc[6 * q + 4]; cp -= dfc[6 * q + 5];
+              }
+#pragma unroll
+              for (int off = TPR; off < 32; off <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, off);
+                ap += __shfl_xor_sync(0xffffffffu, ap, off);
+                b += __shfl_xor_sync(0xffffffffu, b, off);
+                bp += __shfl_xor_sync(0xffffffffu, bp, off);
+              }
+              const int c = 4 * tau + 4 * TPR * h + j;
+              const double l = __ldg(wlp + c), rr = __ldg(wrp + c);
+              if (sub == 0) th_all_acc += l * (double)a * (double)b + rr * (double)ap * (double)bp;
+              th_auto_acc += l * (double)cc + rr * (double)cp;
+            }
+          }
+          team_sync<WORKER>(bar_id);  // nb_s is read before the next time can overwrite it
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tA[q] = tB[q] = tC[q] = (T)0;
+          dirty_time = false;
         }
       }
     }
