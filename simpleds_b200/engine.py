@@ -160,6 +160,8 @@ class RedundantPipeline:
                 raise ValueError("noise='inject' needs noise_in complex64 shaped like vis")
             noise_in = noise_in.contiguous()
         ntot = T if ntime_total is None else int(ntime_total)
+        if T == 0:  # an empty batch of a streamed job adds nothing
+            return
         if self.fused:
             self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
         else:

@@ -231,3 +231,18 @@ def test_chirpz_engine_matches_oracle(cuda_device, N, F0, starts):
         assert_close(parts[key], res[key], 2e-6, what=key)
     pipe128, _ = run_pipeline(a, wins, "complex128", None)
     assert not pipe128.fused
+
+
+def test_fused_engine_empty_batch_is_a_no_op(cuda_device):
+    """A streamed job may hand over a batch with no times; the sums must not move."""
+    a = make_array(5, 1, [3, 2], 2, 256)
+    pipe, before = run_pipeline(a, [(0, 255)], "complex64", "philox")
+    dev = pipe.device
+    z = lambda x: torch.as_tensor(x, device=dev)[:, :, :0].contiguous()  # noqa: E731
+    pipe.process(z(a["vis"]), z(a["flags"]), z(a["nsample"]),
+                 torch.as_tensor(a["int_time"], device=dev)[:, :0].contiguous())
+    torch.cuda.synchronize()
+    after = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in pipe.result().items()}
+    for k, v in before.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, after[k], equal_nan=True), k
