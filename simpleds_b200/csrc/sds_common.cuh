@@ -33,6 +33,21 @@ int cuda_fail(cudaError_t e, const char *where);
     if (e__ != cudaSuccess) return sds::cuda_fail(e__, name);    \
   } while (0)
 
+// ---- per-device one-time kernel configuration ----------------------------------------------
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must set the dynamic
+// shared-memory limit on each of them.  One latch per (kernel instantiation, device); the race
+// of two host threads setting the same attribute twice is benign.
+struct DeviceLatch {
+  bool done[64] = {};
+  bool need(int *dev) {
+    if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= 64) return true;
+    return !done[*dev];
+  }
+  void set(int dev) {
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+};
+
 // ---- complex helpers -------------------------------------------------------
 template <typename T> struct cpx { T x, y; };
 template <typename T> struct vec2;

@@ -513,14 +513,15 @@ static thread_local int g_last_launches = 0;
 template <typename T, int N, int LEGS>
 static int launch_engine(const EngineParams &P, cudaStream_t st) {
   using C = EngCfg<T, N, LEGS>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceLatch configured;
+  int cfg_dev = 0;
+  if (configured.need(&cfg_dev)) {
     SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     // several CTAs per SM only fit when the L1/shared split favours shared memory
     SDS_CUDA(cudaFuncSetAttribute(engine_kernel<T, N, LEGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));

@@ -359,14 +359,15 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
 template <int M, int LEGS>
 static int launch_blue(const EngineParams &P, cudaStream_t st, int *launches) {
   using C = EBCfg<M>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceLatch configured;
+  int cfg_dev = 0;
+  if (configured.need(&cfg_dev)) {
     SDS_CUDA(cudaFuncSetAttribute(engine_blue_kernel<M, LEGS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     SDS_CUDA(cudaFuncSetAttribute(engine_blue_kernel<M, LEGS>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));

@@ -467,14 +467,15 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 template <int N, int LEGS>
 static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
   using C = E3Cfg<N>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceLatch configured;
+  int cfg_dev = 0;
+  if (configured.need(&cfg_dev)) {
     SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     // several CTAs per SM only fit when the L1/shared split favours shared memory
     SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));

@@ -126,14 +126,15 @@ delay_fft_bluestein_kernel(const __grid_constant__ BlueParams<T> P) {
 template <typename T, int M>
 static int launch_blue_m(const BlueParams<T> &P, cudaStream_t st) {
   using C = BlueCfg<T, M>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceLatch configured;
+  int cfg_dev = 0;
+  if (configured.need(&cfg_dev)) {
     SDS_CUDA(cudaFuncSetAttribute(delay_fft_bluestein_kernel<T, M>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     SDS_CUDA(cudaFuncSetAttribute(delay_fft_bluestein_kernel<T, M>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));

@@ -112,14 +112,15 @@ delay_fft_pow2_kernel(const __grid_constant__ Pow2Params<T> P) {
 template <typename T, int N>
 static int launch_pow2_n(const Pow2Params<T> &P, cudaStream_t st) {
   using C = Pow2Cfg<T, N>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceLatch configured;
+  int cfg_dev = 0;
+  if (configured.need(&cfg_dev)) {
     SDS_CUDA(cudaFuncSetAttribute(delay_fft_pow2_kernel<T, N>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     SDS_CUDA(cudaFuncSetAttribute(delay_fft_pow2_kernel<T, N>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));

@@ -246,3 +246,23 @@ def test_fused_engine_empty_batch_is_a_no_op(cuda_device):
     for k, v in before.items():
         if isinstance(v, np.ndarray):
             assert np.array_equal(v, after[k], equal_nan=True), k
+
+
+def test_fused_engine_on_a_second_device_of_the_same_process(cuda_device):
+    """Kernel attributes (dynamic shared memory) are per device: one process driving two GPUs must
+    get the same sums on both."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from simpleds_b200.engine import RedundantPipeline
+    a = make_array(11, 2, [4, 3], 2, 256)
+    out = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            pipe = RedundantPipeline(a["freq"], [(0, 255)], a["pols"], a["group_offset"], trcvr_k=144.0,
+                                     beam_area_sr=0.76, precision="complex64", seed=3)
+            pipe.process(*(torch.as_tensor(a[k], device=dev) for k in ("vis", "flags", "nsample", "int_time")))
+            torch.cuda.synchronize()
+            out.append({k: v.cpu().numpy() for k, v in pipe.result().items() if hasattr(v, "cpu")})
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k], equal_nan=True), k
