@@ -23,15 +23,21 @@ namespace sds {
 #ifndef E3_WARPS_PER_SM
 #define E3_WARPS_PER_SM 12  // register budget: 65536 / (12 * 32) = 170 per thread
 #endif
-template <int N> struct E3Cfg {
+template <int N, int LEGS> struct E3Cfg {
+  // the noise leg alone (complex128 mode) keeps neither visibilities nor the data accumulators:
+  // 122 registers and 5 N staged bytes per row let 16 warps per SM run it
+  static constexpr bool NOISE_ONLY = LEGS == LEG_NOISE;
   static constexpr int TPR = N / 8;                     // threads per row
   static constexpr int TEAM = TPR < 32 ? 32 : TPR;      // threads per worker
   static constexpr int ROWS = TEAM / TPR;               // rows per step
   static constexpr int THREADS = TEAM < E3_MIN_THREADS ? E3_MIN_THREADS : TEAM;
   static constexpr int NWORKER = THREADS / TEAM;
   // resident CTAs per SM the register allocation aims at (12 warps: measured best at N = 256)
-  static constexpr int MINB = (E3_WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (E3_WARPS_PER_SM * 32) / THREADS;
-  static constexpr int ROWB = 13 * N;                   // vis 8N | nsample 4N | flags N
+  // (N = 2048 runs 256-thread CTAs: a second one would halve their registers -- measured slower)
+  static constexpr int WARPS_PER_SM = (NOISE_ONLY && THREADS <= 128) ? 16 : E3_WARPS_PER_SM;
+  static constexpr int MINB = (WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (WARPS_PER_SM * 32) / THREADS;
+  static constexpr int VISB = (LEGS & LEG_DATA) ? 8 * N : 0;
+  static constexpr int ROWB = VISB + 5 * N;             // vis 8N (data leg only) | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = N * 8;                     // one exchange buffer of one row
   static constexpr int XREGION = NWORKER * ROWS * 2 * BUF;  // all exchange buffers, aligned to BUF
@@ -72,13 +78,13 @@ __device__ __forceinline__ bool team_any(bool pred, int barrier_id) {
 }
 
 template <int N, int LEGS>
-__global__ void __launch_bounds__(E3Cfg<N>::THREADS, E3Cfg<N>::MINB)
+__global__ void __launch_bounds__(E3Cfg<N, LEGS>::THREADS, E3Cfg<N, LEGS>::MINB)
 engine_f32_kernel(const __grid_constant__ EngineParams P) {
   // LEGS without LEG_DATA (the noise leg alone) serves the complex128 mode, whose data and
   // thermal legs run in fp64 (sds_engine.cu) while the noise realisation stays fp32
   constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
                  HAS_T = (LEGS & LEG_THERMAL) != 0;
-  using C = E3Cfg<N>;
+  using C = E3Cfg<N, LEGS>;
   using FFT = TeamFftX<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,7 +118,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) tapdf[r] = __ldg(P.taper_f + tau + TPR * r) * (float)P.delta_f;
   const int total_items = P.item_start[P.ngroup];
-  constexpr uint32_t ROW_BYTES = 13 * N;
   const int64_t row_stride = (int64_t)P.ntime * P.nchan;  // samples between baselines
   // the team's first warp stages its rows (warp-uniform test: shfl from lane 0)
   const bool issuer_warp = TEAM == 32 || __shfl_sync(0xffffffffu, tl, 0) == 0;
@@ -158,13 +163,13 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (issuer_warp && elect_one()) {
         const int nact = ROWS == 1 ? 1 : min(ROWS, ng - pi0);
         const uint32_t bar = full_a + 8u * slot_p;
-        mbar_expect_tx_a(bar, (uint32_t)nact * (HAS_D ? ROW_BYTES : 5u * N));
+        mbar_expect_tx_a(bar, (uint32_t)nact * (uint32_t)C::ROWB);
         uint32_t dst = stages_a + slot_p * (uint32_t)C::SLOT;
         int64_t e = pe;
         for (int rr = 0; rr < nact; ++rr, e += row_stride, dst += C::ROWB) {
           if (HAS_D) tma_load_1d_a(dst, P.vis + e, 8 * N, bar);
-          tma_load_1d_a(dst + 8 * N, P.nsample + e, 4 * N, bar);
-          tma_load_1d_a(dst + 12 * N, P.flags + e, N, bar);
+          tma_load_1d_a(dst + C::VISB, P.nsample + e, 4 * N, bar);
+          tma_load_1d_a(dst + C::VISB + 4 * N, P.flags + e, N, bar);
         }
       }
       slot_p = slot_p + 1 == E3_STAGES ? 0 : slot_p + 1;
@@ -242,8 +247,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       mbar_wait_a(full_a + 8u * slot_c, par_c);
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
       const f2 *vis_s = reinterpret_cast<const f2 *>(row) + tau;
-      const float *ns_s = reinterpret_cast<const float *>(row + 8 * N) + tau;
-      const unsigned char *fl_s = row + 12 * N + tau;
+      const float *ns_s = reinterpret_cast<const float *>(row + C::VISB) + tau;
+      const unsigned char *fl_s = row + C::VISB + 4 * N + tau;
 
       // rt = t_int^-1/2, itv = 1 / t_int (0 where the integration time is not positive)
       const float rt = (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
@@ -466,7 +471,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 
 template <int N, int LEGS>
 static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
-  using C = E3Cfg<N>;
+  using C = E3Cfg<N, LEGS>;
   static DeviceLatch configured;
   int cfg_dev = 0;
   if (configured.need(&cfg_dev)) {
