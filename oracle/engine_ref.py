@@ -123,6 +123,49 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
     return (amp * np.cos(ang.astype(np.float64)) + 1j * amp * np.sin(ang.astype(np.float64))).astype(np.complex64)
 
 
+def engine_noise_freq_mm(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
+                         ntime_total=None, bl_offset=0, nbl_total=None):
+    """The frequency-domain noise of the power-of-two engine's production draw (noise_mode 1,
+    csrc/sds_engine.cuh ``engine_word_mm`` / ``engine_signs_mm``), before mask and taper:
+    ``sigma * B * (s1 + i s2)`` with B in {0, 1}, s1, s2 in {-1, +1} -- zero mean, circular,
+    E|n|^2 = sigma^2 and E|n|^4 = 2 sigma^4 like the complex Gaussian of utils.py:501-505.
+
+    One Philox4x32-7 call serves thread tau (channels tau + (N/8) r, r = 0..7) of four consecutive
+    baselines: counter = (blk low word, blk high word, tau, 2),
+    blk = ((s*P + p) * ceil(Bt / 4) + (b >> 2)) * Tt + t with global b, t; baseline b takes word
+    b & 3; bit r of the word is B, bit 8 + r the sign of the real and bit 16 + r of the imaginary part."""
+    P, B, T, _ = nsample.shape
+    S, N = len(win_start), nfreq
+    tpr = N // 8
+    Tt = T if ntime_total is None else ntime_total
+    Bt = B if nbl_total is None else nbl_total
+    nblk = (Bt + 3) // 4
+    s_i, p_i, b_i, t_i, tau_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
+                                            np.arange(tpr), indexing="ij")
+    bg = (b_i + bl_offset).astype(np.uint64)
+    blk = ((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(nblk)
+           + (bg >> np.uint64(2))) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
+    W = philox4x32((blk & _LO).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
+                   tau_i.astype(np.uint32), np.full(blk.shape, 2, np.uint32),
+                   np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),
+                   rounds=ENGINE_PHILOX_ROUNDS)
+    sel = (bg & np.uint64(3)).astype(np.int64)
+    word = np.choose(sel, [w.astype(np.uint32) for w in W])  # (S,P,B,T,tpr)
+    unit = np.zeros((S, P, B, T, N), np.complex128)
+    for r in range(8):
+        on = ((word >> np.uint32(r)) & np.uint32(1)).astype(np.float64)
+        s_re = 1.0 - 2.0 * ((word >> np.uint32(8 + r)) & np.uint32(1)).astype(np.float64)
+        s_im = 1.0 - 2.0 * ((word >> np.uint32(16 + r)) & np.uint32(1)).astype(np.float64)
+        unit[..., np.arange(tpr) + tpr * r] = on * (s_re + 1j * s_im)
+    chans = np.asarray(win_start)[:, None] + np.arange(N)
+    ns_w = np.stack([nsample[..., chans[s]] for s in range(S)]).astype(np.float64)  # (S,P,B,T,N)
+    tn = int_time[None, None, :, :, None].astype(np.float64) * ns_w
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = sigma_coef32[:, :, None, None, :].astype(np.float64) / np.sqrt(tn)
+    amp = np.where(tn > 0, amp, 0.0)
+    return (amp * unit).astype(np.complex64)
+
+
 def engine_noise_freq_chirpz(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
                              ntime_total=None, bl_offset=0, nbl_total=None):
     """The noise of the chirp-z engine (window lengths that are not powers of two,

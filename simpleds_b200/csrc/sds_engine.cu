@@ -591,7 +591,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   SDS_CHECK_ARG(d->npol >= 1 && d->nbl >= 1 && d->ntime >= 1 && d->ngroup >= 1 && d->nspw >= 1 &&
                     d->nspw <= SDS_MAX_WINDOWS && d->ngroup <= 65535,
                 "sds_engine_run: bad dimensions");
-  SDS_CHECK_ARG(d->noise_mode >= 0 && d->noise_mode <= 2, "sds_engine_run: noise_mode not in 0..2");
+  SDS_CHECK_ARG(d->noise_mode >= 0 && d->noise_mode <= 3, "sds_engine_run: noise_mode not in 0..3");
   SDS_CHECK_ARG(d->noise_mode == 0 || (int_time && sigma_coef && noise_all && noise_auto),
                 "sds_engine_run: noise needs int_time, sigma_coef and the noise outputs");
   SDS_CHECK_ARG(d->noise_mode != 2 || noise_in, "sds_engine_run: noise_mode 2 needs noise_in");
@@ -647,7 +647,11 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   P.delta_f = d->delta_f; P.seed_lo = (uint32_t)d->seed; P.seed_hi = (uint32_t)(d->seed >> 32);
   philox_fill_keys(P.seed_lo, P.seed_hi, P.pkey);
   P.npol = d->npol; P.nbl = d->nbl; P.ntime = d->ntime; P.nchan = d->nchan; P.nspw = d->nspw;
-  P.ngroup = d->ngroup; P.noise_mode = d->noise_mode;
+  P.ngroup = d->ngroup;
+  // in-kernel draws: mode 1 = moment-matched discrete law (power-of-two engine; the chirp-z engine
+  // draws Box-Muller in both modes), mode 3 = Box-Muller per channel
+  P.noise_mode = d->noise_mode == 3 ? 1 : d->noise_mode;
+  P.noise_gauss = d->noise_mode == 3;
   P.target_rows = 64;
   for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
   P.nfreq = N;

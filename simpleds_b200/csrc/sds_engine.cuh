@@ -34,6 +34,7 @@ struct EngineParams {
   uint32_t seed_lo, seed_hi;
   uint32_t pkey[16];          // Philox round keys: pkey[2 r] = seed_lo + r W0, pkey[2 r + 1] = seed_hi + r W1
   int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
+  int noise_gauss;            // noise_mode 1: 0 = moment-matched discrete draw (engine_draw_mm), 1 = Box-Muller (engine_draw8)
   int win_start[SDS_MAX_WINDOWS];
   // windows whose length is not a power of two (sds_engine_blue.cu): chirp-z tables of the plan
   int nfreq;                  // window length N
@@ -216,6 +217,47 @@ __device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, const uin
       sn[2 * m + h] = fast_sin(ang);
     }
   }
+}
+
+// ---- the production draw of the power-of-two engine: moment-matched discrete noise ------------
+// The engine never exposes the frequency-domain noise; what leaves it are delay-domain pair sums,
+// i.e. sums over >= 64 tapered channels of every row.  By the central limit theorem the law of the
+// transformed noise is fixed by the per-channel moments, so the per-channel draw is the cheapest law
+// that matches the complex Gaussian sigma (g1 + i g2) / sqrt(2) of utils.py:501-505 in every moment
+// the pair sums see at leading order:
+//     n[c] = sigma[c] * B * (s1 + i s2),   B in {0, 1} (p = 1/2),  s1, s2 in {-1, +1}
+//   E n = 0,  E n^2 = 0 (circular),  E |n|^2 = sigma^2,  E |n|^4 = 2 sigma^4 (= the Gaussian value;
+//   a uniform or a constant-modulus draw has 1.4 and 1), so that mean AND variance of every |X[k]|^2
+//   and of every cross product agree with the Gaussian realisation up to O(1 / N_eff^2)
+//   (tests/test_gpu_noise_stats.py measures them).  The covariance between delay bins -- taper, flag
+//   comb and nsample profile of the row -- is exact, because the per-channel amplitudes are.
+// Three random bits per sample and no arithmetic: the on/off bit rides on the flag select, the two
+// signs are XOR-ed into the amplitude.  One Philox4x32-7 call serves the same thread of FOUR
+// consecutive baselines: counter = (blk low word, blk high word, tau, 2) with
+//   blk = ((s npol + p) ceil(nbl_total / 4) + (b >> 2)) ntime_total + t      (b, t global indices)
+// and baseline b takes word b & 3 of the call.  Bits of the word, for the thread's channel tau + TPR r:
+//   bit r: on / off,  bit 8 + r: sign of the real part,  bit 16 + r: sign of the imaginary part.
+struct NoiseWords {
+  u32x4 w;
+  uint32_t tag_lo, tag_hi;  // blk of the cached call
+};
+template <int ROUNDS>
+__device__ __forceinline__ uint32_t engine_word_mm(NoiseWords &c, uint64_t blk, uint32_t sel, int tau,
+                                                   const uint32_t (&key)[16]) {
+  if ((uint32_t)blk != c.tag_lo || (uint32_t)(blk >> 32) != c.tag_hi) {  // uniform over a row team
+    c.w = philox4x32_keyed<ROUNDS>({(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)tau, 2u}, key);
+    c.tag_lo = (uint32_t)blk;
+    c.tag_hi = (uint32_t)(blk >> 32);
+  }
+  const uint32_t a = (sel & 1u) ? c.w.y : c.w.x, b = (sel & 1u) ? c.w.w : c.w.z;
+  return (sel & 2u) ? b : a;
+}
+// (re, im) = (+-amp, +-amp) for sample r of the word
+__device__ __forceinline__ unsigned long long engine_signs_mm(float amp, uint32_t word, int r) {
+  const uint32_t ab = __float_as_uint(amp);
+  const uint32_t re = ab ^ ((word << (23 - r)) & 0x80000000u);
+  const uint32_t im = ab ^ ((word << (15 - r)) & 0x80000000u);
+  return (unsigned long long)re | ((unsigned long long)im << 32);
 }
 
 // chunk(g) = clamp(target_rows / n_g, 1, ntime); items(g) = ceil(ntime / chunk) nspw npol

@@ -23,7 +23,9 @@ namespace sds {
 #ifndef E3_WARPS_PER_SM
 #define E3_WARPS_PER_SM 12  // register budget: 65536 / (12 * 32) = 170 per thread
 #endif
-template <int N, int LEGS> struct E3Cfg {
+// GAUSS: the in-kernel draw is Box-Muller per channel (noise_mode 3) instead of the moment-matched
+// discrete law (noise_mode 1); injected noise (mode 2) runs in the GAUSS = false instantiation
+template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // the noise leg alone (complex128 mode) keeps neither visibilities nor the data accumulators:
   // 122 registers and 5 N staged bytes per row let 16 warps per SM run it
   static constexpr bool NOISE_ONLY = LEGS == LEG_NOISE;
@@ -77,14 +79,14 @@ __device__ __forceinline__ bool team_any(bool pred, int barrier_id) {
   }
 }
 
-template <int N, int LEGS>
-__global__ void __launch_bounds__(E3Cfg<N, LEGS>::THREADS, E3Cfg<N, LEGS>::MINB)
+template <int N, int LEGS, bool GAUSS>
+__global__ void __launch_bounds__(E3Cfg<N, LEGS, GAUSS>::THREADS, E3Cfg<N, LEGS, GAUSS>::MINB)
 engine_f32_kernel(const __grid_constant__ EngineParams P) {
   // LEGS without LEG_DATA (the noise leg alone) serves the complex128 mode, whose data and
   // thermal legs run in fp64 (sds_engine.cu) while the noise realisation stays fp32
   constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
                  HAS_T = (LEGS & LEG_THERMAL) != 0;
-  using C = E3Cfg<N, LEGS>;
+  using C = E3Cfg<N, LEGS, GAUSS>;
   using FFT = TeamFftX<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -191,7 +193,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       for (int r = 0; r < 8; ++r) {
         if (P.noise_mode == 1) {
           const float c = __ldg(P.sigma_coef + ((int64_t)s * P.npol + p) * N + tau + TPR * r);
-          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * ENG_SQRT_LN2 * tapdf[r] : 0.f;
+          sigc[r] = (fabsf(c) <= 3.0e38f) ? c * (GAUSS ? ENG_SQRT_LN2 : 1.f) * tapdf[r] : 0.f;
         } else {
           sigc[r] = tapdf[r];
         }
@@ -225,6 +227,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
                        (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
                       (uint64_t)(P.time_offset + t0));
 
+    // moment-matched draw: the Philox call of the current block of four baselines
+    NoiseWords nwords;
+    nwords.tag_lo = nwords.tag_hi = 0xFFFFFFFFu;
+    const uint64_t nblk = (uint64_t)((P.nbl_total + 3) >> 2);
+    const uint64_t blk_sp = (uint64_t)((int64_t)s * P.npol + p) * nblk;
     for (int k = 0; k < E3_STAGES - 1 && pleft > 0; ++k) issue();
     // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
     // on the critical path of every row)
@@ -243,6 +250,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         const int ni = (wrap ? 0 : ci0 + ROWS) + sub;
         tint_next = __ldg(P.int_time + it_off + (wrap ? 1 : 0) +
                           (int64_t)((ROWS == 1 || ni < ng) ? ni : 0) * P.ntime);
+        // keep the value in a vector register: for warp-sized teams it is warp-uniform, and a
+        // uniform register would be waited on right behind the load instead of one step later
+        asm volatile("" : "+f"(tint_next));
       }
       mbar_wait_a(full_a + 8u * slot_c, par_c);
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
@@ -270,7 +280,20 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       f2 vd[8], vn[8];
       // mask = (1 - flag) (ds.py:3503-3505); taper and delta_f ride on the same multiplier
       // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
-      if (HAS_N && P.noise_mode == 1) {
+      if (HAS_N && !GAUSS && P.noise_mode == 1) {
+        const uint64_t bglob = (uint64_t)(P.bl_offset + b0 + ia);
+        const uint64_t blk = (blk_sp + (bglob >> 2)) * (uint64_t)P.ntime_total + (uint64_t)(P.time_offset + ct);
+        const uint32_t word = engine_word_mm<ENG_PHILOX_ROUNDS>(nwords, blk, (uint32_t)bglob & 3u, tau, P.pkey);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const bool k = active && fl_s[TPR * r] == 0;
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
+          // sigma = coef / sqrt(t_int nsample) (ds.py:3546-3581); the on/off bit rides on the flag select
+          const bool kn = k && ((word >> r) & 1u);
+          const float amp = ((kn ? sigc[r] : 0.f) * rt) * av[r];
+          vn[r] = engine_signs_mm(amp, word, r);
+        }
+      } else if (HAS_N && GAUSS && P.noise_mode == 1) {
         float rad[8], cs[8], sn[8];
         engine_draw8<TPR>(rid_t + (uint64_t)ia * (uint64_t)P.ntime_total, tau, P.pkey, rad, cs, sn);
 #pragma unroll
@@ -469,29 +492,29 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   }
 }
 
-template <int N, int LEGS>
+template <int N, int LEGS, bool GAUSS = false>
 static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
-  using C = E3Cfg<N, LEGS>;
+  using C = E3Cfg<N, LEGS, GAUSS>;
   static DeviceLatch configured;
   int cfg_dev = 0;
   if (configured.need(&cfg_dev)) {
-    SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS>,
+    SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS, GAUSS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     // several CTAs per SM only fit when the L1/shared split favours shared memory
-    SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    SDS_CUDA(cudaFuncSetAttribute(engine_f32_kernel<N, LEGS, GAUSS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
     configured.set(cfg_dev);
   }
   int dev = 0, nsm = 148, per_sm = 1;
   SDS_CUDA(cudaGetDevice(&dev));
   SDS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  SDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, engine_f32_kernel<N, LEGS>,
+  SDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, engine_f32_kernel<N, LEGS, GAUSS>,
                                                          C::THREADS, C::SMEM));
   if (per_sm < 1) {
     set_error("sds_engine_run: kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
   }
-  engine_f32_kernel<N, LEGS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
+  engine_f32_kernel<N, LEGS, GAUSS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
   SDS_LAUNCH_CHECK("engine_f32_kernel");
   ++*launches;
   return SDS_OK;
@@ -499,6 +522,14 @@ static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
 
 template <int N>
 static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *launches) {
+  if (P.noise_mode == 1 && P.noise_gauss) {
+    switch (legs) {
+      case 2: return launch_f32<N, 2, true>(P, st, launches);
+      case 3: return launch_f32<N, 3, true>(P, st, launches);
+      case 7: return launch_f32<N, 7, true>(P, st, launches);
+      default: break;
+    }
+  }
   switch (legs) {
     case 1: return launch_f32<N, 1>(P, st, launches);
     case 2: return launch_f32<N, 2>(P, st, launches);

@@ -256,21 +256,31 @@ template <int N> struct TeamFftX {
     return A;
   }
 
+  // twiddles of pass P (P > 0) into registers; called BEFORE the exchange that precedes the pass, so
+  // that the loads do not queue behind the sixteen loads of the exchange (the table is read-only)
+  template <int P>
+  static __device__ __forceinline__ void load_tw(f2 (&w)[7], const f2 *__restrict__ tw, int tau) {
+    constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P);
+    constexpr int OFF = fft_tw_offset(N, P);
+    // the twiddle of butterfly j depends on j % NS only: with NS < TPR the lanes of a warp read
+    // NS distinct words (a broadcast: fewer shared-memory wavefronts than TPR distinct ones)
+    const int tt = (NB == 1 && NS < TPR) ? (tau & (NS - 1)) : tau;
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+#pragma unroll
+      for (int q = 1; q < R; ++q) w[m * (R - 1) + (q - 1)] = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tt];
+  }
   template <int P, bool TWO>
   static __device__ __forceinline__ void pass(f2 (&a)[8], f2 (&b)[8], const Addr &A,
-                                              const f2 *__restrict__ tw, int tau, int bar) {
+                                              const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7]) {
     constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
     static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
     if constexpr (P > 0) {
-      constexpr int OFF = fft_tw_offset(N, P);
-      // the twiddle of butterfly j depends on j % NS only: with NS < TPR the lanes of a warp read
-      // NS distinct words (a broadcast: fewer shared-memory wavefronts than TPR distinct ones)
-      const int tt = (NB == 1 && NS < TPR) ? (tau & (NS - 1)) : tau;
 #pragma unroll
       for (int m = 0; m < NB; ++m)
 #pragma unroll
         for (int q = 1; q < R; ++q) {
-          const f2 w = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tt];
+          const f2 w = wp[m * (R - 1) + (q - 1)];
           a[m + NB * q] = f2_cmul(a[m + NB * q], w);
           if (TWO) b[m + NB * q] = f2_cmul(b[m + NB * q], w);
         }
@@ -301,6 +311,8 @@ template <int N> struct TeamFftX {
       }
     }
     if constexpr (P < NPASS - 1) {
+      f2 wn[7];
+      load_tw<P + 1>(wn, tw, tau);
       team_sync<WORKER>(bar);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -309,18 +321,20 @@ template <int N> struct TeamFftX {
         if (TWO) b[r] = lds_f2_off<BUFB>(ad);
       }
       if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
-      pass<P + 1, TWO>(a, b, A, tw, tau, bar);
+      pass<P + 1, TWO>(a, b, A, tw, tau, bar, wn);
     }
   }
   // NOTE: the caller must team-sync between two calls on the same buffers (the engine's step
   // loop does, at the top of every step).
   static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], const Addr &A,
                                               const f2 *__restrict__ tw, int tau, int bar) {
-    pass<0, true>(a, b, A, tw, tau, bar);
+    const f2 w0[7] = {};
+    pass<0, true>(a, b, A, tw, tau, bar, w0);
   }
   static __device__ __forceinline__ void run(f2 (&a)[8], const Addr &A, const f2 *__restrict__ tw,
                                              int tau, int bar) {
-    pass<0, false>(a, a, A, tw, tau, bar);
+    const f2 w0[7] = {};
+    pass<0, false>(a, a, A, tw, tau, bar, w0);
   }
 };
 

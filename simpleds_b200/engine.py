@@ -140,7 +140,9 @@ class RedundantPipeline:
                 thermal=True, noise_in=None):
         """Accumulate one batch of times.  vis complex64 (P,B,T,Nchan); flags bool/uint8
         and nsample float32 of the same shape; int_time float32 (B,T).  ``noise``:
-        "philox" (in-kernel realisation), None, or "inject" with ``noise_in`` (a
+        "philox" (in-kernel realisation: the moment-matched discrete draw of
+        csrc/sds_engine.cuh in the power-of-two engine), "philox_gauss" (in-kernel
+        Box-Muller draw per channel), None, or "inject" with ``noise_in`` (a
         frequency-domain noise array shaped like vis; parity tests)."""
         P, B, T, F0 = vis.shape
         if (P, B, F0) != (self.npol, self.nbl, self.nchan):
@@ -154,7 +156,7 @@ class RedundantPipeline:
         if fl.dtype != torch.uint8:
             raise ValueError("flags must be bool or uint8")
         vis, fl, nsample, int_time = vis.contiguous(), fl.contiguous(), nsample.contiguous(), int_time.contiguous()
-        mode = {None: 0, "philox": 1, "inject": 2}[noise]
+        mode = {None: 0, "philox": 1, "inject": 2, "philox_gauss": 3}[noise]
         if mode == 2:
             if noise_in is None or tuple(noise_in.shape) != tuple(vis.shape) or noise_in.dtype != torch.complex64:
                 raise ValueError("noise='inject' needs noise_in complex64 shaped like vis")
@@ -214,7 +216,7 @@ class RedundantPipeline:
         it64 = int_time.to(torch.float64)
         if mode:
             fl_w = ops.take_windows(fl[None], chans)
-            if mode == 1:
+            if mode in (1, 3):
                 sig = ops.noise_sigma(self.sigma_coef64, it64, ns_w[:, None])
                 # one Philox stream per batch (the fused path's stream is keyed by
                 # global sample coordinates instead; both are valid realisations)
@@ -267,7 +269,7 @@ class RedundantPipeline:
         if (P, B, F0) != (self.npol, self.nbl, self.nchan) or tuple(ins["int_time"].shape) != (B, T) \
                 or tuple(ins["flags"].shape) != (P, B, T, F0) or tuple(ins["nsample"].shape) != (P, B, T, F0):
             raise ValueError("host arrays do not match the pipeline's (Npols, Nbls, T, Nchan)")
-        mode = {None: 0, "philox": 1}[noise]
+        mode = {None: 0, "philox": 1, "philox_gauss": 3}[noise]
         ntot = T if ntime_total is None else int(ntime_total)
         dev = self.device
         if not self.fused:  # any window length: one upload, chained kernels

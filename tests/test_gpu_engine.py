@@ -93,17 +93,23 @@ def test_fused_engine_matches_oracle_injected_noise(cuda_device, N, nwin, precis
     assert np.abs(res["power_all"].imag).max() == 0
 
 
-@pytest.mark.parametrize("N,precision", [(256, "complex64"), (128, "complex128")])
-def test_fused_engine_philox_noise_matches_restated_stream(cuda_device, N, precision):
-    group_sizes = [4, 7, 1]
+@pytest.mark.parametrize("N,precision,mode", [(256, "complex64", "philox"), (128, "complex128", "philox"),
+                                              (1024, "complex64", "philox"), (64, "complex64", "philox"),
+                                              (256, "complex64", "philox_gauss"), (128, "complex128", "philox_gauss")])
+def test_fused_engine_philox_noise_matches_restated_stream(cuda_device, N, precision, mode):
+    """Both in-kernel draws against their restated streams (oracle/engine_ref.py), value by value
+    through the noise pair sums: "philox" = the moment-matched discrete law, "philox_gauss" =
+    Box-Muller per channel."""
+    group_sizes = [4, 7, 1, 6]
     a = make_array(7, 2, group_sizes, 3, 2 * N, zero_ns_frac=0.02)
     wins = [(0, N - 1), (N, 2 * N - 1)]
-    pipe, res = run_pipeline(a, wins, precision, "philox", seed=0x1234567890)
-    noise_freq = engine_ref.engine_noise_freq(pipe.sigma_coef32.cpu().numpy(), a["nsample"], a["int_time"],
-                                              pipe.win_start, N, 0x1234567890)
+    pipe, res = run_pipeline(a, wins, precision, mode, seed=0x1234567890)
+    restate = engine_ref.engine_noise_freq if mode == "philox_gauss" else engine_ref.engine_noise_freq_mm
+    noise_freq = restate(pipe.sigma_coef32.cpu().numpy(), a["nsample"], a["int_time"], pipe.win_start, N,
+                         0x1234567890)
     ref = engine_ref.group_means(a["vis"], a["flags"], a["nsample"], a["int_time"], a["group_offset"],
                                  a["freq"], wins, a["pols"], 144.0, 0.76, noise_freq=noise_freq)
-    # fast-math log/sincos in the kernel vs numpy: 1e-4 of the row maximum
+    # fast-math rsqrt (and log/sincos for Box-Muller) in the kernel vs numpy: 1e-4 of the row maximum
     check_against_oracle(res, ref, group_sizes, 2.5e-5, ["noise_power_all", "noise_power_noautos"])
     # sigma of the reference's radiometer equation is what the stream is scaled by
     sig = ref["sigma"][1]  # (S,P,B,T,N) of group 1
