@@ -237,19 +237,13 @@ __device__ __forceinline__ void engine_draw8(uint64_t row_id, int tau, const uin
 //   blk = ((s npol + p) ceil(nbl_total / 4) + (b >> 2)) ntime_total + t      (b, t global indices)
 // and baseline b takes word b & 3 of the call.  Bits of the word, for the thread's channel tau + TPR r:
 //   bit r: on / off,  bit 8 + r: sign of the real part,  bit 16 + r: sign of the imaginary part.
-struct NoiseWords {
-  u32x4 w;
-  uint32_t tag_lo, tag_hi;  // blk of the cached call
-};
+// the call of block `blk`, and word `sel` of it
 template <int ROUNDS>
-__device__ __forceinline__ uint32_t engine_word_mm(NoiseWords &c, uint64_t blk, uint32_t sel, int tau,
-                                                   const uint32_t (&key)[16]) {
-  if ((uint32_t)blk != c.tag_lo || (uint32_t)(blk >> 32) != c.tag_hi) {  // uniform over a row team
-    c.w = philox4x32_keyed<ROUNDS>({(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)tau, 2u}, key);
-    c.tag_lo = (uint32_t)blk;
-    c.tag_hi = (uint32_t)(blk >> 32);
-  }
-  const uint32_t a = (sel & 1u) ? c.w.y : c.w.x, b = (sel & 1u) ? c.w.w : c.w.z;
+__device__ __forceinline__ u32x4 engine_call_mm(uint64_t blk, int tau, const uint32_t (&key)[16]) {
+  return philox4x32_keyed<ROUNDS>({(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)tau, 2u}, key);
+}
+__device__ __forceinline__ uint32_t engine_pick_mm(const u32x4 &w, uint32_t sel) {
+  const uint32_t a = (sel & 1u) ? w.y : w.x, b = (sel & 1u) ? w.w : w.z;
   return (sel & 2u) ? b : a;
 }
 // (re, im) = (+-amp, +-amp) for sample r of the word

@@ -228,8 +228,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
                       (uint64_t)(P.time_offset + t0));
 
     // moment-matched draw: the Philox call of the current block of four baselines
-    NoiseWords nwords;
-    nwords.tag_lo = nwords.tag_hi = 0xFFFFFFFFu;
+    u32x4 nwords = {0u, 0u, 0u, 0u};
     const uint64_t nblk = (uint64_t)((P.nbl_total + 3) >> 2);
     const uint64_t blk_sp = (uint64_t)((int64_t)s * P.npol + p) * nblk;
     for (int k = 0; k < E3_STAGES - 1 && pleft > 0; ++k) issue();
@@ -281,9 +280,15 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       // mask = (1 - flag) (ds.py:3503-3505); taper and delta_f ride on the same multiplier
       // (utils.py:552-560): tapdf for the data, sigc (= sigma coefficient * tapdf) for the noise
       if (HAS_N && !GAUSS && P.noise_mode == 1) {
-        const uint64_t bglob = (uint64_t)(P.bl_offset + b0 + ia);
-        const uint64_t blk = (blk_sp + (bglob >> 2)) * (uint64_t)P.ntime_total + (uint64_t)(P.time_offset + ct);
-        const uint32_t word = engine_word_mm<ENG_PHILOX_ROUNDS>(nwords, blk, (uint32_t)bglob & 3u, tau, P.pkey);
+        // a new block of four baselines starts at the first step of a time and whenever the
+        // (global) baseline index crosses a multiple of four; uniform over the row team
+        const uint32_t bsel = (uint32_t)(P.bl_offset + b0 + ia) & 3u;
+        if (ci0 == 0 || bsel < (uint32_t)ROWS) {
+          const uint64_t bglob = (uint64_t)(P.bl_offset + b0 + ia);
+          const uint64_t blk = (blk_sp + (bglob >> 2)) * (uint64_t)P.ntime_total + (uint64_t)(P.time_offset + ct);
+          nwords = engine_call_mm<ENG_PHILOX_ROUNDS>(blk, tau, P.pkey);
+        }
+        const uint32_t word = engine_pick_mm(nwords, bsel);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const bool k = active && fl_s[TPR * r] == 0;
