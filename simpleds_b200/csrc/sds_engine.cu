@@ -652,6 +652,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   // draws Box-Muller in both modes), mode 3 = Box-Muller per channel
   P.noise_mode = d->noise_mode == 3 ? 1 : d->noise_mode;
   P.noise_gauss = d->noise_mode == 3;
+  P.zero = 0;
   P.target_rows = 64;
   for (int i = 0; i < SDS_MAX_WINDOWS; ++i) P.win_start[i] = i < d->nspw ? d->win_start[i] : 0;
   P.nfreq = N;

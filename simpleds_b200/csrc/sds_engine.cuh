@@ -34,6 +34,7 @@ struct EngineParams {
   uint32_t seed_lo, seed_hi;
   uint32_t pkey[16];          // Philox round keys: pkey[2 r] = seed_lo + r W0, pkey[2 r + 1] = seed_hi + r W1
   int npol, nbl, ntime, nchan, nspw, ngroup, noise_mode, target_rows;
+  int zero;                   // always 0: lets a kernel form addresses ptxas cannot prove warp-uniform
   int noise_gauss;            // noise_mode 1: 0 = moment-matched discrete draw (engine_draw_mm), 1 = Box-Muller (engine_draw8)
   int win_start[SDS_MAX_WINDOWS];
   // windows whose length is not a power of two (sds_engine_blue.cu): chirp-z tables of the plan

@@ -98,6 +98,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
     tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
+  // 0 at run time (P.zero is 0), lane-dependent as far as ptxas can tell: see the int_time load
+  const int lane_zero = (int)(threadIdx.x & 31u) * P.zero;
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;
   // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
   const uint32_t xa = smem_u32(smem) + (uint32_t)((wid * ROWS + sub) * 2) * C::BUF;
@@ -247,11 +249,12 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if ((HAS_N || HAS_T) && step + 1 < nsteps) {
         const bool wrap = ci0 + ROWS >= ng;
         const int ni = (wrap ? 0 : ci0 + ROWS) + sub;
-        tint_next = __ldg(P.int_time + it_off + (wrap ? 1 : 0) +
+        // lane_zero (= 0 at run time, but lane-dependent as far as ptxas can tell) keeps the address, and with it
+        // the loaded value, out of the uniform datapath: for warp-sized teams the value is
+        // warp-uniform, and a uniform register is waited on right behind the load (R2UR) instead of
+        // one step later (10 % of the issue stalls, profiles/r2_engine_mm3)
+        tint_next = __ldg(P.int_time + it_off + (wrap ? 1 : 0) + lane_zero +
                           (int64_t)((ROWS == 1 || ni < ng) ? ni : 0) * P.ntime);
-        // keep the value in a vector register: for warp-sized teams it is warp-uniform, and a
-        // uniform register would be waited on right behind the load instead of one step later
-        asm volatile("" : "+f"(tint_next));
       }
       mbar_wait_a(full_a + 8u * slot_c, par_c);
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
