@@ -183,6 +183,13 @@ typedef struct sds_engine_desc {
   int64_t nbl_total;   /* global number of baselines                            */
   uint64_t seed;
   double delta_f;      /* Hz, scales the transform (utils.py:560)               */
+  /* A sub-list of the redundant groups (sharding by group, delay_spectrum.py:891-900: every group
+   * is its own object): the arrays hold only the baselines of `ngroup` chosen groups.  Device
+   * pointers, both NULL for the whole list:
+   *   group_index[g]    row of the output arrays group g accumulates into,
+   *   group_bl_start[g] index of the group's first baseline in the whole array (RNG counter). */
+  const int32_t *group_index;
+  const int64_t *group_bl_start;
 } sds_engine_desc;
 
 /* In-kernel noise (noise_mode 1), replacing utils.py:486-506 + ds.py:3544-3583: every

@@ -31,6 +31,7 @@ class EngineDesc(C.Structure):
         ("time_offset", C.c_int64), ("ntime_total", C.c_int64),
         ("bl_offset", C.c_int64), ("nbl_total", C.c_int64),
         ("seed", C.c_uint64), ("delta_f", C.c_double),
+        ("group_index", C.c_void_p), ("group_bl_start", C.c_void_p),
     ]
 
 

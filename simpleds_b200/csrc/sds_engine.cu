@@ -179,6 +179,10 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       if (__ldg(P.item_start + mid) <= item) lo = mid; else hi = mid;
     }
     const int g = lo, b0 = __ldg(P.goff + g), ng = __ldg(P.goff + g + 1) - b0;
+    // a sub-list of groups (group sharding): where the group's sums go and where its baselines sit
+    // in the whole array (the noise stream is keyed by the global baseline index)
+    const int gout = P.group_id ? __ldg(P.group_id + g) : g;
+    const int64_t blg = P.group_bl0 ? __ldg(P.group_bl0 + g) : P.bl_offset + b0;
     const int chunk = eng_chunk(ng, P.ntime, P.target_rows);
     const int nchunks = (P.ntime + chunk - 1) / chunk;
     const int local = item - __ldg(P.item_start + g);
@@ -249,7 +253,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
     // Philox counter base of (row 0, time t0): row_id * N/2, row_id = ((s npol + p) nbl_total + b) ntime_total + t (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
-                       (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
+                       (uint64_t)blg) * (uint64_t)P.ntime_total +
                       (uint64_t)(P.time_offset + t0));
 
     for (int k = 0; k < C::STAGES - 1 && pleft > 0; ++k) issue();
@@ -450,7 +454,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     }
 
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
-    const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
+    const int64_t obase = (((int64_t)gout * P.nspw + s) * P.npol + p) * N;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int kshift = (tau + TPR * r + N / 2) % N;
@@ -481,7 +485,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       }
       if ((wl & 31) == 0) {
         const double f = 1e-6 * __ldg(P.pol_factor + p);
-        const int64_t o = ((int64_t)g * P.nspw + s) * P.npol + p;
+        const int64_t o = ((int64_t)gout * P.nspw + s) * P.npol + p;
         atomicAdd(P.th_all + o, f * th_all_acc);
         atomicAdd(P.th_auto + o, f * th_auto_acc);
       }
@@ -634,7 +638,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   EngWorkspace ws = carve(workspace, d->ngroup, d->nspw, d->npol, N);
   EngineParams P;
   P.vis = (const float2 *)vis; P.flags = flags; P.nsample = nsample; P.int_time = int_time;
-  P.goff = group_offset; P.sigma_coef = sigma_coef; P.noise_in = (const float2 *)noise_in;
+  P.goff = group_offset; P.group_id = d->group_index; P.group_bl0 = d->group_bl_start; P.sigma_coef = sigma_coef; P.noise_in = (const float2 *)noise_in;
   P.pol_factor = pol_factor;
   P.taper_f = pl.taper_f; P.tw_f = (const float2 *)pl.team_tw_f;
   if (pl.math == SDS_F64) { P.taper = pl.taper_d; P.tw = pl.team_tw_d; }

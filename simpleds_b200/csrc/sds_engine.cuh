@@ -17,6 +17,8 @@ struct EngineParams {
   const float *nsample;
   const float *int_time;
   const int32_t *goff;
+  const int32_t *group_id;    // [ngroup] output index of each group, or NULL (identity)
+  const int64_t *group_bl0;   // [ngroup] global index of each group's first baseline, or NULL (bl_offset + goff)
   const float *sigma_coef;
   const float2 *noise_in;
   const double *pol_factor;

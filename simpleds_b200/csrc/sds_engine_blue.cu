@@ -113,6 +113,10 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
       if (__ldg(P.item_start + mid) <= item) lo = mid; else hi = mid;
     }
     const int g = lo, b0 = __ldg(P.goff + g), ng = __ldg(P.goff + g + 1) - b0;
+    // a sub-list of groups (group sharding): where the group's sums go and where its baselines sit
+    // in the whole array (the noise stream is keyed by the global baseline index)
+    const int gout = P.group_id ? __ldg(P.group_id + g) : g;
+    const int64_t blg = P.group_bl0 ? __ldg(P.group_bl0 + g) : P.bl_offset + b0;
     const int chunk = eng_chunk(ng, P.ntime, P.target_rows);
     const int nchunks = (P.ntime + chunk - 1) / chunk;
     const int local = item - __ldg(P.item_start + g);
@@ -120,7 +124,7 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
     const int t0 = tc * chunk, t1 = min(P.ntime, t0 + chunk);
     const int steps_per_t = (ng + ROWS - 1) / ROWS, nsteps = (t1 - t0) * steps_per_t;
     const int64_t e00 = (((int64_t)p * P.nbl + b0) * P.ntime + t0) * P.nchan + P.win_start[s];
-    const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
+    const int64_t obase = (((int64_t)gout * P.nspw + s) * P.npol + p) * N;
 
     int pi0 = 0, pleft = nsteps;
     int64_t pe = e00, pe_t = e00;
@@ -176,7 +180,7 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
     int ci0 = 0, ct = t0;
     int64_t it_off = (int64_t)b0 * P.ntime + t0;
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
-                       (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
+                       (uint64_t)blg) * (uint64_t)P.ntime_total +
                       (uint64_t)(P.time_offset + t0));
 
     for (int k = 0; k < EB_STAGES - 1 && pleft > 0; ++k) issue();
@@ -348,7 +352,7 @@ engine_blue_kernel(const __grid_constant__ EngineParams P) {
       }
       if ((tl & 31) == 0) {
         const double f = 1e-6 * __ldg(P.pol_factor + p);
-        const int64_t o = ((int64_t)g * P.nspw + s) * P.npol + p;
+        const int64_t o = ((int64_t)gout * P.nspw + s) * P.npol + p;
         atomicAdd(P.th_all + o, f * th_all_acc);
         atomicAdd(P.th_auto + o, f * th_auto_acc);
       }

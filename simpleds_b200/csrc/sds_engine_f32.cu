@@ -148,6 +148,10 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (__ldg(P.item_start + mid) <= item) lo = mid; else hi = mid;
     }
     const int g = lo, b0 = __ldg(P.goff + g), ng = __ldg(P.goff + g + 1) - b0;
+    // a sub-list of groups (group sharding): where the group's sums go and where its baselines sit
+    // in the whole array (the noise stream is keyed by the global baseline index)
+    const int gout = P.group_id ? __ldg(P.group_id + g) : g;
+    const int64_t blg = P.group_bl0 ? __ldg(P.group_bl0 + g) : P.bl_offset + b0;
     const int chunk = eng_chunk(ng, P.ntime, P.target_rows);
     const int nchunks = (P.ntime + chunk - 1) / chunk;
     const int local = item - __ldg(P.item_start + g);
@@ -156,7 +160,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     const int steps_per_t = (ng + ROWS - 1) / ROWS, nsteps = (t1 - t0) * steps_per_t;
     // sample offset of (pol p, first baseline of the group, time t0, window start)
     const int64_t e00 = (((int64_t)p * P.nbl + b0) * P.ntime + t0) * P.nchan + P.win_start[s];
-    const int64_t obase = (((int64_t)g * P.nspw + s) * P.npol + p) * N;
+    const int64_t obase = (((int64_t)gout * P.nspw + s) * P.npol + p) * N;
 
     // ---- producer state (one elected lane stages rows i0 .. i0+ROWS-1 of time t) ----------
     int pi0 = 0;          // first row of the next step to stage
@@ -226,7 +230,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // Philox counter words 0, 1 of (row 0, time t0):
     // row_id = ((s npol + p) nbl_total + b) ntime_total + t   (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
-                       (uint64_t)(P.bl_offset + b0)) * (uint64_t)P.ntime_total +
+                       (uint64_t)blg) * (uint64_t)P.ntime_total +
                       (uint64_t)(P.time_offset + t0));
 
     // moment-matched draw: the Philox call of the current block of four baselines
@@ -285,9 +289,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (HAS_N && !GAUSS && P.noise_mode == 1) {
         // a new block of four baselines starts at the first step of a time and whenever the
         // (global) baseline index crosses a multiple of four; uniform over the row team
-        const uint32_t bsel = (uint32_t)(P.bl_offset + b0 + ia) & 3u;
+        const uint32_t bsel = (uint32_t)(blg + ia) & 3u;
         if (ci0 == 0 || bsel < (uint32_t)ROWS) {
-          const uint64_t bglob = (uint64_t)(P.bl_offset + b0 + ia);
+          const uint64_t bglob = (uint64_t)(blg + ia);
           const uint64_t blk = (blk_sp + (bglob >> 2)) * (uint64_t)P.ntime_total + (uint64_t)(P.time_offset + ct);
           nwords = engine_call_mm<ENG_PHILOX_ROUNDS>(blk, tau, P.pkey);
         }
@@ -492,7 +496,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if ((tl & 31) == 0) {
         const double f = 1e-6 * __ldg(P.pol_factor + p);
-        const int64_t o = ((int64_t)g * P.nspw + s) * P.npol + p;
+        const int64_t o = ((int64_t)gout * P.nspw + s) * P.npol + p;
         atomicAdd(P.th_all + o, f * th_all_acc);
         atomicAdd(P.th_auto + o, f * th_auto_acc);
       }

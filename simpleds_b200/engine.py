@@ -132,21 +132,38 @@ class RedundantPipeline:
         self.noise_auto = torch.zeros(shape, dtype=torch.float64, device=dev)
         self.thermal_all = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
         self.thermal_auto = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
-        self.ntimes_done = 0
+        # times accumulated per group: travels with the sums through reduce(), so that result() is
+        # right whichever way the job was sharded (times split over ranks add up, groups dealt to
+        # ranks are disjoint)
+        self.times_done = torch.zeros(self.ngroup, dtype=torch.float64, device=dev)
+        self.ntimes_done = 0  # times this process has passed to process() (bookkeeping only)
         self._ws = None
 
     # ------------------------------------------------------------------ one batch
     def process(self, vis, flags, nsample, int_time, time_offset=0, ntime_total=None, noise="philox",
-                thermal=True, noise_in=None):
+                thermal=True, noise_in=None, groups=None):
         """Accumulate one batch of times.  vis complex64 (P,B,T,Nchan); flags bool/uint8
         and nsample float32 of the same shape; int_time float32 (B,T).  ``noise``:
         "philox" (in-kernel realisation: the moment-matched discrete draw of
         csrc/sds_engine.cuh in the power-of-two engine), "philox_gauss" (in-kernel
         Box-Muller draw per channel), None, or "inject" with ``noise_in`` (a
-        frequency-domain noise array shaped like vis; parity tests)."""
+        frequency-domain noise array shaped like vis; parity tests).
+
+        ``groups``: rising indices of the redundant groups this call covers (sharding by
+        group: every group is its own object in the reference, ds.py:891-900).  The arrays
+        then hold only the baselines of those groups, in that order; the other groups' sums
+        are not touched and the noise stream stays keyed by the global baseline index.
+
+        A streamed job passes ``time_offset`` (global index of the batch's first time) and
+        ``ntime_total``: the in-kernel noise is a function of the global (baseline, time)
+        coordinates, so batches and shards of one job realise one and the same noise field."""
         P, B, T, F0 = vis.shape
-        if (P, B, F0) != (self.npol, self.nbl, self.nchan):
-            raise ValueError(f"vis has shape {tuple(vis.shape)}, expected ({self.npol}, {self.nbl}, T, {self.nchan})")
+        sub = None
+        if groups is not None:
+            sub = self._group_subset(groups)
+        nbl_expect = self.nbl if sub is None else sub["nbl"]
+        if (P, B, F0) != (self.npol, nbl_expect, self.nchan):
+            raise ValueError(f"vis has shape {tuple(vis.shape)}, expected ({self.npol}, {nbl_expect}, T, {self.nchan})")
         if tuple(flags.shape) != tuple(vis.shape) or tuple(nsample.shape) != tuple(vis.shape) \
                 or tuple(int_time.shape) != (B, T):
             raise ValueError("flags/nsample must match vis and int_time must be (Nbls, Ntimes)")
@@ -161,26 +178,69 @@ class RedundantPipeline:
             if noise_in is None or tuple(noise_in.shape) != tuple(vis.shape) or noise_in.dtype != torch.complex64:
                 raise ValueError("noise='inject' needs noise_in complex64 shaped like vis")
             noise_in = noise_in.contiguous()
-        ntot = T if ntime_total is None else int(ntime_total)
+        time_offset = int(time_offset)
+        if ntime_total is None:
+            if time_offset != 0:
+                raise ValueError("a batch with time_offset > 0 needs ntime_total (the noise counters are keyed "
+                                 "by the global time index)")
+            ntot = T
+        else:
+            ntot = int(ntime_total)
+        if time_offset < 0 or time_offset + T > ntot:
+            raise ValueError(f"times [{time_offset}, {time_offset + T}) do not fit ntime_total = {ntot}")
         if T == 0:  # an empty batch of a streamed job adds nothing
             return
+        if sub is not None and len(sub["index"]) == 0:
+            return
         if self.fused:
-            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
+            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot,
+                                subset=sub)
         else:
+            if sub is not None:
+                raise NotImplementedError("groups= needs the fused path (aligned windows of a supported length)")
             self._process_unfused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot)
+        if sub is None:
+            self.times_done += T
+        else:
+            self.times_done[sub["index_dev"].long()] += T
         self.ntimes_done += T
 
+    def _group_subset(self, groups):
+        """Device tables of a rising list of group indices (cached): local group offsets, output
+        rows, global first-baseline indices."""
+        key = tuple(int(g) for g in groups)
+        cache = self.__dict__.setdefault("_subsets", {})
+        if key not in cache:
+            idx = np.asarray(key, dtype=np.int64)
+            if idx.size and (np.any(np.diff(idx) <= 0) or idx[0] < 0 or idx[-1] >= self.ngroup):
+                raise ValueError("groups must be rising indices of redundant groups")
+            sizes = self.group_sizes[idx] if idx.size else np.zeros(0, np.int64)
+            dev = self.device
+            cache[key] = dict(
+                index=idx, nbl=int(sizes.sum()),
+                goff_dev=torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32), device=dev),
+                index_dev=torch.as_tensor(idx.astype(np.int32), device=dev),
+                bl0_dev=torch.as_tensor(self.group_offset_host[idx].astype(np.int64), device=dev),
+            )
+        return cache[key]
+
     def _process_fused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot,
-                       groups=None):
+                       groups=None, subset=None):
         """One sds_engine_run.  ``groups`` = (g0, g1, goff_dev): the arrays hold only the
-        baselines of redundant groups g0..g1-1 (a chunk of process_host); the noise
-        counters stay keyed by the global baseline index."""
+        baselines of redundant groups g0..g1-1 (a chunk of process_host); ``subset``: the
+        tables of an arbitrary rising list of groups (_group_subset).  The noise counters
+        stay keyed by the global baseline index."""
         lib = _lib.load()
         P, B, T, F0 = vis.shape
         g0, g1, goff = (0, self.ngroup, self.group_offset) if groups is None else groups
         d = EngineDesc()
         d.npol, d.nbl, d.ntime, d.nchan = P, B, T, F0
         d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, g1 - g0, 1, mode
+        if subset is not None:
+            g0, g1, goff = 0, self.ngroup, subset["goff_dev"]
+            d.ngroup = len(subset["index"])
+            d.group_index = subset["index_dev"].data_ptr()
+            d.group_bl_start = subset["bl0_dev"].data_ptr()
         for i, w in enumerate(self.win_start):
             d.win_start[i] = w
         d.time_offset, d.ntime_total = int(time_offset), ntot
@@ -251,11 +311,13 @@ class RedundantPipeline:
         return chunks
 
     def process_host(self, vis, flags, nsample, int_time, time_offset=0, ntime_total=None, noise="philox",
-                     thermal=True, chunk_bytes=1 << 29):
+                     thermal=True, chunk_bytes=1 << 29, fetch=True):
         """``process`` for HOST arrays (numpy or CPU torch tensors; pinned memory makes the
         copies asynchronous): the baselines are cut into chunks of whole redundant groups,
         chunk k+1 is uploaded on a copy stream while chunk k runs, and ``result_host()``
-        is returned (pinned host buffers viewed as numpy arrays)."""
+        is returned (pinned host buffers viewed as numpy arrays).  A streamed job passes
+        ``fetch=False`` for every batch (nothing is copied back, nothing is waited for) and
+        calls ``result_host()`` once at its end."""
         ins = {}
         for name, a, dt in (("vis", vis, torch.complex64), ("flags", flags, torch.uint8),
                             ("nsample", nsample, torch.float32), ("int_time", int_time, torch.float32)):
@@ -270,13 +332,18 @@ class RedundantPipeline:
                 or tuple(ins["flags"].shape) != (P, B, T, F0) or tuple(ins["nsample"].shape) != (P, B, T, F0):
             raise ValueError("host arrays do not match the pipeline's (Npols, Nbls, T, Nchan)")
         mode = {None: 0, "philox": 1, "philox_gauss": 3}[noise]
+        if ntime_total is None and int(time_offset) != 0:
+            raise ValueError("a batch with time_offset > 0 needs ntime_total")
         ntot = T if ntime_total is None else int(ntime_total)
+        if int(time_offset) < 0 or int(time_offset) + T > ntot:
+            raise ValueError(f"times [{time_offset}, {int(time_offset) + T}) do not fit ntime_total = {ntot}")
         dev = self.device
         if not self.fused:  # any window length: one upload, chained kernels
             d = [ins[k].to(dev, non_blocking=True) for k in ("vis", "flags", "nsample", "int_time")]
             self._process_unfused(*d, mode, None, thermal, time_offset, ntot)
             self.ntimes_done += T
-            return self.result_host()
+            self.times_done += T
+            return self.result_host() if fetch else None
 
         chunks = self._host_chunks(T, chunk_bytes)
         go = self.group_offset_host
@@ -315,7 +382,8 @@ class RedundantPipeline:
                                 time_offset, ntot, groups=(g0, g1, self._goff_chunks[(g0, g1)]))
             st["done"].record(cur)
         self.ntimes_done += T
-        return self.result_host()
+        self.times_done += T
+        return self.result_host() if fetch else None
 
     def result_host(self, ntimes=None):
         """``result()`` copied into (cached) pinned host buffers; numpy views are returned."""
@@ -336,7 +404,10 @@ class RedundantPipeline:
         return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
     def reduce(self, dst=0, all_ranks=False):
-        """Sum the ranks' partial accumulators (one collective; see shard.reduce_partials)."""
+        """Sum the ranks' partial accumulators and their per-group time counts (one
+        collective on one flat buffer; see shard.reduce_partials).  Afterwards ``result()``
+        on ``dst`` (every rank with ``all_ranks``) is the result of the whole job, whether
+        the ranks split the times or the groups."""
         from . import shard
 
         shard.reduce_partials(self.sums(), dst=dst, all_ranks=all_ranks)
@@ -346,22 +417,26 @@ class RedundantPipeline:
         """Raw accumulators (what ranks reduce over NVLink)."""
         return dict(pow_all=self.pow_all, pow_auto=self.pow_auto, noise_all=self.noise_all,
                     noise_auto=self.noise_auto, thermal_all=self.thermal_all,
-                    thermal_auto=self.thermal_auto)
+                    thermal_auto=self.thermal_auto, times_done=self.times_done)
 
     def result(self, ntimes=None):
         """Means over ordered baseline pairs and times, per (group, spw, pol[, delay]).
 
         ``*_all``: every ordered pair (i, j), autos included (tutorial cell 41);
         ``*_noautos``: i != j (utils.remove_auto_correlations); NaN for 1-baseline groups."""
-        T = self.ntimes_done if ntimes is None else ntimes
         n = torch.as_tensor(self.group_sizes, dtype=torch.float64, device=self.device)
-        n4, n3 = n.view(-1, 1, 1, 1), n.view(-1, 1, 1)
+        # per-group count of accumulated times (NaN for a group that saw none), or the caller's
+        tg = torch.where(self.times_done > 0, self.times_done, torch.full_like(self.times_done, float("nan")))
+        if ntimes is not None:
+            tg = torch.full_like(self.times_done, float(ntimes))
+        n4, n3, T4, T3 = n.view(-1, 1, 1, 1), n.view(-1, 1, 1), tg.view(-1, 1, 1, 1), tg.view(-1, 1, 1)
         out = {}
+        nan = torch.full((), float("nan"), dtype=torch.float64, device=self.device)  # one baseline: no cross pairs
         for key, a, b in (("power", self.pow_all, self.pow_auto), ("noise_power", self.noise_all, self.noise_auto)):
-            out[key + "_all"] = a / (n4 * n4 * T)
-            out[key + "_noautos"] = (a - b) / (n4 * (n4 - 1) * T)
-        out["thermal_all"] = self.thermal_all / (n3 * n3 * T)
-        out["thermal_noautos"] = (self.thermal_all - self.thermal_auto) / (n3 * (n3 - 1) * T)
+            out[key + "_all"] = a / (n4 * n4 * T4)
+            out[key + "_noautos"] = torch.where(n4 > 1, (a - b) / (n4 * (n4 - 1) * T4), nan)
+        out["thermal_all"] = self.thermal_all / (n3 * n3 * T3)
+        out["thermal_noautos"] = torch.where(n3 > 1, (self.thermal_all - self.thermal_auto) / (n3 * (n3 - 1) * T3), nan)
         out["delay_array_ns"] = self.delay_array_ns
         return out
 

@@ -22,6 +22,9 @@ import torch
 import torch.distributed as dist
 
 SUM_KEYS = ("pow_all", "pow_auto", "noise_all", "noise_auto", "thermal_all", "thermal_auto")
+# per-group count of accumulated times: rides in the same flat buffer when present, so that the
+# reduced means are right for time shards (counts add up) and group shards (disjoint) alike
+OPTIONAL_KEYS = ("times_done",)
 
 
 def time_shards(ntimes, world):
@@ -63,7 +66,7 @@ def choose_partition(ntimes, group_sizes, world):
 def pack_sums(sums):
     """Flatten the accumulator dict (SUM_KEYS order) into one fp64 vector + its layout."""
     parts, layout = [], []
-    for k in SUM_KEYS:
+    for k in SUM_KEYS + tuple(k for k in OPTIONAL_KEYS if k in sums):
         t = sums[k]
         if t.is_complex():
             t = torch.view_as_real(t)

@@ -34,7 +34,7 @@ def test_engine_desc_layout_matches_header():
     from simpleds_b200 import _lib
 
     # 8 int32 + 64 int32 + 4 int64 + uint64 + double
-    assert ctypes.sizeof(_lib.EngineDesc) == 8 * 4 + 64 * 4 + 4 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.EngineDesc) == 8 * 4 + 64 * 4 + 4 * 8 + 8 + 8 + 2 * 8
 
 
 def test_plan_argument_errors_surface_as_valueerror():

@@ -272,3 +272,39 @@ def test_fused_engine_on_a_second_device_of_the_same_process(cuda_device):
             out.append({k: v.cpu().numpy() for k, v in pipe.result().items() if hasattr(v, "cpu")})
     for k in out[0]:
         assert np.array_equal(out[0][k], out[1][k], equal_nan=True), k
+
+
+def test_fused_engine_group_subsets_equal_the_whole_job(cuda_device):
+    """Sharding by redundant group (every group is its own object in the reference,
+    ds.py:891-900): two calls that each hold ONLY the baselines of their groups give the sums of
+    the whole job -- noise included, its stream being keyed by the global baseline index -- and a
+    process that saw only some groups reports NaN means for the others."""
+    from simpleds_b200.engine import RedundantPipeline
+
+    group_sizes = [6, 1, 9, 3, 17, 2]
+    a = make_array(91, 2, group_sizes, 3, 512, zero_ns_frac=0.02)
+    wins = [(0, 255), (256, 511)]
+    whole_pipe, whole = run_pipeline(a, wins, "complex64", "philox", seed=5)
+    dev = torch.device("cuda:0")
+    pipe = RedundantPipeline(a["freq"], wins, a["pols"], a["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                             precision="complex64", seed=5)
+    go = a["group_offset"]
+    for mine in ([0, 2, 3], [1, 4, 5]):
+        bl = np.concatenate([np.arange(go[g], go[g + 1]) for g in mine])
+        pipe.process(torch.as_tensor(a["vis"][:, bl], device=dev), torch.as_tensor(a["flags"][:, bl], device=dev),
+                     torch.as_tensor(a["nsample"][:, bl], device=dev), torch.as_tensor(a["int_time"][bl], device=dev),
+                     noise="philox", groups=mine)
+        if mine == [0, 2, 3]:
+            part = pipe.result()
+            assert bool(torch.isnan(part["power_all"][1]).all()) and bool(torch.isfinite(part["power_all"][0]).all())
+    torch.cuda.synchronize()
+    for k, v in whole_pipe.sums().items():
+        np.testing.assert_allclose(pipe.sums()[k].cpu().numpy(), v.cpu().numpy(), rtol=1e-12, atol=0, err_msg=k)
+    with pytest.raises(ValueError):
+        pipe.process(torch.as_tensor(a["vis"], device=dev), torch.as_tensor(a["flags"], device=dev),
+                     torch.as_tensor(a["nsample"], device=dev), torch.as_tensor(a["int_time"], device=dev),
+                     groups=[2, 1])
+    with pytest.raises(ValueError):  # a later batch of a streamed job must say how long the job is
+        pipe.process(torch.as_tensor(a["vis"], device=dev), torch.as_tensor(a["flags"], device=dev),
+                     torch.as_tensor(a["nsample"], device=dev), torch.as_tensor(a["int_time"], device=dev),
+                     time_offset=3)

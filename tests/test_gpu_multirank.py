@@ -1,7 +1,8 @@
 """Two ranks, two GPUs, NCCL: the sharded job on the real kernels.
 
 Each rank runs the fused engine on its shard -- half of the times (noise counters keyed by the
-global time index), or the redundant groups the partitioner deals it -- and ONE reduce of the
+global time index), or ONLY the baselines of the redundant groups the partitioner deals it
+(``process(..., groups=mine)``) -- and ONE reduce of the
 partial sums closes the job; rank 0 then holds the sums of the one-GPU job: equal up to the
 order of the additions (fp32 partial sums per time chunk for time shards; only the fp64 atomics
 for group shards, whose results are disjoint).  Skipped on boxes with fewer than two GPUs (the driver's one-GPU tier); the CPU suite
@@ -61,19 +62,19 @@ def _worker(rank, world, port, mode, out_path):
                          torch.as_tensor(a["nsample"][:, :, sl], device=dev), torch.as_tensor(a["int_time"][:, sl], device=dev),
                          time_offset=t0, ntime_total=T)
         else:
-            mine = set(shard.group_shards(GROUP_SIZES, world)[rank])
-            # this rank's groups keep their data; the others' visibilities are zeroed and their
-            # sums discarded below, so the reduce acts as a gather of disjoint results
-            pipe.process(*(torch.as_tensor(a[k], device=dev) for k in ("vis", "flags", "nsample", "int_time")),
-                         time_offset=0, ntime_total=T)
-            for k, v in pipe.sums().items():
-                for g in range(len(GROUP_SIZES)):
-                    if g not in mine:
-                        v[g] = 0
+            # this rank holds and processes ONLY the baselines of the groups the partitioner deals it
+            mine = shard.group_shards(GROUP_SIZES, world)[rank]
+            go = a["group_offset"]
+            bl = np.concatenate([np.arange(go[g], go[g + 1]) for g in mine])
+            pipe.process(torch.as_tensor(a["vis"][:, bl], device=dev), torch.as_tensor(a["flags"][:, bl], device=dev),
+                         torch.as_tensor(a["nsample"][:, bl], device=dev), torch.as_tensor(a["int_time"][bl], device=dev),
+                         time_offset=0, ntime_total=T, groups=mine)
         pipe.reduce(dst=0)
         torch.cuda.synchronize()
         if rank == 0:
-            torch.save({k: v.cpu() for k, v in pipe.sums().items()}, out_path)
+            out = {k: v.cpu() for k, v in pipe.sums().items()}
+            out.update({"result_" + k: v.cpu() for k, v in pipe.result().items() if hasattr(v, "cpu")})
+            torch.save(out, out_path)
     finally:
         dist.destroy_process_group()
 
@@ -95,8 +96,26 @@ def test_two_gpu_nccl_reduce_equals_the_one_gpu_job(cuda_device, tmp_path, mode)
     torch.cuda.synchronize()
     for k, v in pipe.sums().items():
         want = v.cpu().numpy()
-        if mode == "group":  # disjoint results; only the order of the fp64 atomic additions differs
+        if mode == "group" or k == "times_done":  # disjoint results; only the order of the fp64 atomic additions differs
             np.testing.assert_allclose(got[k].numpy(), want, rtol=1e-12, atol=0, err_msg=k)
         else:  # the same additions in another order (fp32 partial sums per time chunk, fp64 atomics)
             scale = np.abs(want).max(axis=-1, keepdims=True) if want.ndim == 4 else np.abs(want)
             assert np.all(np.abs(got[k].numpy() - want) <= 2e-6 * scale + 1e-300), k
+    # the documented flow `pipe.reduce(dst=0); res = pipe.result()` gives the one-GPU means (the
+    # per-group time counts travel with the sums)
+    res = {k: v.cpu().numpy() for k, v in pipe.result().items() if hasattr(v, "cpu")}
+    sums = {k: v.cpu().numpy() for k, v in pipe.sums().items()}
+    n = np.asarray(GROUP_SIZES, dtype=np.float64)
+    for base, ka, kb in (("power", "pow_all", "pow_auto"), ("noise_power", "noise_all", "noise_auto"),
+                         ("thermal", "thermal_all", "thermal_auto")):
+        a_all, a_auto = sums[ka], sums[kb]
+        shp = (-1,) + (1,) * (a_all.ndim - 1)
+        top = (lambda x: np.abs(x).max(axis=-1, keepdims=True)) if a_all.ndim == 4 else np.abs
+        # the sums agree to 2e-6 of their row maximum (above); the means inherit that error
+        tol_all = 4e-6 * top(a_all) / (n.reshape(shp) ** 2 * T)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tol_no = 4e-6 * (top(a_all) + top(a_auto)) / (n.reshape(shp) * (n.reshape(shp) - 1) * T)
+        for key, tol in ((base + "_all", tol_all), (base + "_noautos", tol_no)):
+            want = res[key]
+            err = np.abs(got["result_" + key].numpy() - want)
+            assert np.all((err <= tol + 1e-300) | np.isnan(want)), key
