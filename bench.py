@@ -35,11 +35,21 @@ CONFIGS = {
     # name: (array, nchan, nwin, npol, f0, df, t_int)
     "hera350": dict(array="hera_350", nchan=1024, nwin=4, npol=4, f0=100e6, df=97656.25, t_int=10.7,
                     pols=[-5, -6, -7, -8], seed=1003),
+    # BASELINE.json configs[1]: 203 channels.  The fused path stages rows in 16-channel units, so the
+    # row pitch is 208 channels and the ONE spectral window is channels 0..202 (nfreq = 203)
     "paper64": dict(array="paper_grid", nchan=208, nwin=1, npol=2, f0=100e6, df=492610.84375, t_int=42.95,
-                    pols=[1, 2], seed=1002),
+                    pols=[1, 2], seed=1002, windows=[(0, 202)]),
     "ska512": dict(array="ska_512", nchan=2048, nwin=1, npol=2, f0=50e6, df=146484.375, t_int=0.85,
                    pols=[-5, -6], seed=1005),
 }
+
+
+def config_windows(cfg):
+    """Inclusive (start, end) channel ranges of the configuration's spectral windows."""
+    if "windows" in cfg:
+        return [tuple(w) for w in cfg["windows"]]
+    n = cfg["nchan"] // cfg["nwin"]
+    return [(w * n, (w + 1) * n - 1) for w in range(cfg["nwin"])]
 
 
 def peaks():
@@ -60,8 +70,7 @@ def _cpu_sample_inputs(cfg, n, ntime, seed=0):
     flags = rng.random(shape) < 0.06
     ns = rng.integers(32, 61, shape).astype(np.float64)
     freq = (cfg["f0"] + cfg["df"] * np.arange(F))[None]
-    N = F // cfg["nwin"]
-    wins = [(w * N, (w + 1) * N - 1) for w in range(cfg["nwin"])]
+    wins = config_windows(cfg)
     return dict(vis=vis, flags=flags, nsample=ns, freq_array_hz=freq, trcvr_k=np.full((1, F), 144.0),
                 beam_area_sr=np.full((1, P, F), 0.76), integration_time_s=np.full((n, ntime), cfg["t_int"]),
                 polarization_array=np.array(cfg["pols"]), spectral_windows=wins)
@@ -99,7 +108,7 @@ def cpu_reference_rate(cfg, n, ntime, procs):
         for j in jobs:
             _cpu_chunk(j)
     dt = time.perf_counter() - t0
-    pairs = n * n * cfg["nwin"] * cfg["npol"] * ntime
+    pairs = n * n * len(config_windows(cfg)) * cfg["npol"] * ntime
     return pairs / dt, dt
 
 
@@ -116,9 +125,11 @@ def run_reference_arm(args, cfg):
         r, dt = cpu_reference_rate(cfg, n, ntime, cores)
         rates.append(r)
         times.append(dt)
-    value = float(np.sum([n * n * cfg["nwin"] * cfg["npol"] * ntime] * len(times)) / np.sum(times))
-    sample = (f"one redundant group of {n} baselines x {cfg['npol']} pols x {cfg['nwin']} windows of "
-              f"{cfg['nchan'] // cfg['nwin']} ch x {ntime} times per step, split over {cores} processes by time; "
+    wins = config_windows(cfg)
+    value = float(np.sum([n * n * len(wins) * cfg["npol"] * ntime] * len(times)) / np.sum(times))
+    sample = (f"one redundant group of {n} baselines x {cfg['npol']} pols x {len(wins)} windows of "
+              f"{wins[0][1] - wins[0][0] + 1} ch x {ntime} times per step, split over {cores} processes by time; "
+              "rate per pair-spectrum extrapolated to the whole array (quadratic in the group size); "
               "oracle port of the reference's numpy path incl. noise draw, thermal estimate and the mean")
     line = dict(
         impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times),
@@ -234,6 +245,78 @@ class ClockSampler:
         return out
 
 
+def measure_mode(name, precision, times, steps, dev, peak):
+    """One more BASELINE.json configuration measured in the same run (few steps): the fused path
+    on a resident batch of `times` integrations, all three legs, device-timed like the headline."""
+    import torch
+
+    from simpleds_b200 import synth
+    from simpleds_b200.engine import RedundantPipeline
+
+    cfg = CONFIGS[name]
+    lattice, basis = getattr(synth, cfg["array"])()
+    red = synth.redundant_groups(lattice, basis)
+    freq = cfg["f0"] + cfg["df"] * np.arange(cfg["nchan"])
+    wins = config_windows(cfg)
+    pipe = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                             precision=precision, seed=0)
+    data = synth.make_visibilities(red["group_offset"], cfg["npol"], times, freq, seed=cfg["seed"], device=dev,
+                                   t_int=cfg["t_int"])
+    out = time_pipeline(pipe, data, times, steps, peak)
+    out.update(config=name, precision=precision, nfreq=pipe.nfreq, nbls=pipe.nbl, ngroups=pipe.ngroup,
+               fused=bool(pipe.fused), times_per_step=times)
+    del data, pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_pipeline(pipe, data, times, steps, peak, warmup=3):
+    import torch
+
+    vis, flags, nsample, int_time = data
+    for _ in range(warmup):
+        pipe.process(vis, flags, nsample, int_time, ntime_total=1000)
+    torch.cuda.synchronize()
+    l0 = pipe.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pipe.process(vis, flags, nsample, int_time, ntime_total=1000)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    alg = pipe.algorithmic_bytes(times)
+    return dict(kernel_ms=ms, bytes_per_launch=alg, achieved=alg / (ms * 1e-3) / 1e9,
+                frac=alg / (ms * 1e-3) / 1e9 / peak, value=pipe.pair_spectra(times) / (ms * 1e-3), unit=UNIT,
+                steps=steps, launches_per_step=(pipe.kernel_launches - l0) // steps)
+
+
+def h2d_ceiling(dev, world):
+    """Pinned-host -> device copy rate of this rank while every rank copies at once (GB/s): the
+    ceiling of the end-to-end number, a property of the box's PCIe / host-memory fabric."""
+    import torch
+    import torch.distributed as dist
+
+    n = 1 << 30
+    src = torch.empty(n, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    gbs = 3 * n / (time.perf_counter() - t0) / 1e9
+    if world > 1:
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gbs = float(t.item())
+    del src, dst
+    return gbs
+
+
 def run_gpu_arm(args, cfg):
     import torch
     import torch.distributed as dist
@@ -253,9 +336,10 @@ def run_gpu_arm(args, cfg):
 
     lattice, basis = getattr(synth, cfg["array"])()
     red = synth.redundant_groups(lattice, basis)
-    F, N = cfg["nchan"], cfg["nchan"] // cfg["nwin"]
+    F = cfg["nchan"]
     freq = cfg["f0"] + cfg["df"] * np.arange(F)
-    wins = [(w * N, (w + 1) * N - 1) for w in range(cfg["nwin"])]
+    wins = config_windows(cfg)
+    N = wins[0][1] - wins[0][0] + 1
     pipe = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
                              precision=args.precision, seed=0)
     T = args.times
@@ -366,6 +450,82 @@ def run_gpu_arm(args, cfg):
             step(i)
         torch.cuda.synchronize()
 
+    # the fixed 1000-time job (BASELINE.json configs[2] / [3]): its 1000 / T batches dealt to the
+    # ranks, one reduce at the end; at N = 1 this is the sustained number of the whole job, over N
+    # it is the STRONG scaling of the path (the headline `value` is weak scaling).  Clocks sampled.
+    fixed_job = None
+    if not args.no_fixed_job and not (args.no_noise or args.no_thermal):
+        keep = {k: v.clone() for k, v in pipe.sums().items()}
+        pipe.reset()
+        nbatch = max(ntime_total // T, 1)
+        mine = list(range(rank, nbatch, world))
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        m0 = sampler2.mark() if rank == 0 else 0
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for k in mine:
+            pipe.process(vis, flags, nsample, int_time, time_offset=k * T, ntime_total=ntime_total,
+                         noise="philox", thermal=True)
+        job_reduce()
+        f1.record()
+        torch.cuda.synchronize()
+        job_ms = f0.elapsed_time(f1)
+        if world > 1:
+            tmax = torch.tensor([job_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            job_ms = float(tmax.item())
+        if rank == 0:
+            m1 = sampler2.mark()
+            sampler2.stop()
+            fixed_job = dict(times=nbatch * T, batches=nbatch, batches_on_rank0=len(mine), seconds=job_ms * 1e-3,
+                             value=pipe.pair_spectra(nbatch * T) / (job_ms * 1e-3), unit=UNIT,
+                             frac_of_hbm_peak_per_gpu=pipe.algorithmic_bytes(T) * len(mine) / (job_ms * 1e-3) / 1e9 / peak,
+                             scaling="strong", clocks=sampler2.summary(m0, m1))
+        for k, v in pipe.sums().items():
+            v.copy_(keep[k])
+
+    # N > 1: the reduced sums of a small sharded job against rank 0 doing the same job alone
+    multi_gpu_check = None
+    if world > 1 and not args.no_check:
+        chk = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                                precision=args.precision, seed=3)
+
+        def one(r, pl):
+            d = synth.make_visibilities(red["group_offset"], cfg["npol"], 1, freq, seed=cfg["seed"] + 17,
+                                        device=dev, t_int=cfg["t_int"], time_offset=2000 + r)
+            pl.process(*d, time_offset=r, ntime_total=world, noise="philox", thermal=True)
+            del d
+
+        one(rank, chk)
+        chk.reduce(dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            alone = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                                      precision=args.precision, seed=3)
+            for r in range(world):
+                one(r, alone)
+            torch.cuda.synchronize()
+            worst = 0.0
+            for k, v in alone.sums().items():
+                ref = v.abs().amax(dim=-1, keepdim=True) if v.ndim == 4 else v.abs()
+                err = ((chk.sums()[k] - v).abs() / ref.clamp_min(1e-300)).max()
+                worst = max(worst, float(err.item()))
+            res_c, res_a = chk.result(), alone.result()
+            rel = float(((res_c["power_all"] - res_a["power_all"]).abs().amax(dim=-1)
+                         / res_a["power_all"].abs().amax(dim=-1)).max().item())
+            multi_gpu_check = dict(max_rel_err=worst, result_power_all_max_rel_err=rel,
+                                   what=f"{world} ranks x 1 time each (whole array), NCCL reduce to rank 0, against "
+                                        "rank 0 running the same times alone; error relative to each row's maximum")
+            del alone
+        del chk
+        dist.barrier()
+        torch.cuda.empty_cache()
+
     # end to end through the public API with pinned HOST buffers (H2D + D2H timed), every rank
     e2e = None
     if not args.no_e2e:
@@ -374,6 +534,18 @@ def run_gpu_arm(args, cfg):
         for k, v in pipe.sums().items():
             v.copy_(res_keep[k])
         pipe.ntimes_done = args.steps * T
+
+    # the other BASELINE.json configurations, same run, few steps each (rank 0 of a 1-GPU run)
+    modes = None
+    if world == 1 and not args.no_modes and args.config == "hera350" and args.precision == "complex64":
+        modes = {}
+        p128 = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                                 precision="complex128", seed=0)
+        m = time_pipeline(p128, (vis, flags, nsample, int_time), T, 5, peak)
+        m.update(config="hera350", precision="complex128", nfreq=p128.nfreq, nbls=p128.nbl, ngroups=p128.ngroup,
+                 fused=bool(p128.fused), times_per_step=T)
+        modes["hera350_complex128"] = m
+        del p128
 
     line = None
     if rank == 0:
@@ -393,8 +565,15 @@ def run_gpu_arm(args, cfg):
             dtype="f32" if args.precision == "complex64" else "f64", data="synthetic",
             config=workload_config(args, cfg, pipe), roofline=roofline, cpu_baseline=cpu, e2e=e2e,
             gpu_launches=int(launches), clocks=clocks, outputs_finite=finite,
-            input_gb_per_step_per_gpu=alg_bytes / 1e9,
+            input_gb_per_step_per_gpu=alg_bytes / 1e9, fixed_job=fixed_job, multi_gpu_check=multi_gpu_check,
         )
+        if modes is not None:
+            del vis, flags, nsample, int_time, pipe
+            torch.cuda.empty_cache()
+            modes["ska512_complex64"] = measure_mode("ska512", "complex64", 2, 5, dev, peak)
+            modes["ska512_complex128"] = measure_mode("ska512", "complex128", 2, 3, dev, peak)
+            modes["paper64_203ch_complex64"] = measure_mode("paper64", "complex64", 100, 10, dev, peak)
+            line["roofline"]["modes"] = modes
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -426,10 +605,18 @@ def run_e2e(args, cfg, pipe, red, freq, dev, world=1, rank=0):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    ceiling = h2d_ceiling(dev, world)
+    pipe.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    # a streamed job: every step uploads its batch from pinned host memory and runs it; the job's
+    # result (the per-group means) is read back into pinned host memory ONCE, at its end
     t0 = time.perf_counter()
-    for _ in range(steps):
-        pipe.reset()
-        out = pipe.process_host(*host, noise=None if args.no_noise else "philox", thermal=not args.no_thermal)
+    for i in range(steps):
+        pipe.process_host(*host, time_offset=i * Te, ntime_total=steps * Te,
+                          noise=None if args.no_noise else "philox", thermal=not args.no_thermal, fetch=False)
+    out = pipe.result_host()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     if world > 1:
@@ -438,10 +625,14 @@ def run_e2e(args, cfg, pipe, red, freq, dev, world=1, rank=0):
         dt = float(tmax.item())
     d2h = sum(v.nbytes for v in out.values() if hasattr(v, "nbytes"))
     return dict(value=world * pipe.pair_spectra(Te) / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
-                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * dt, times_per_step_per_gpu=Te, steps=steps,
-                h2d_gbs_per_gpu=(h2d + d2h) / dt / 1e9,
-                note="pinned host buffers -> chunked H2D on a copy stream overlapped with the fused "
-                     "engine -> D2H of the per-group means into pinned buffers; PCIe-bound")
+                d2h_bytes_per_step=int(d2h // steps), d2h_bytes_per_job=int(d2h), ms_per_step=1e3 * dt,
+                times_per_step_per_gpu=Te, steps=steps,
+                h2d_gbs_per_gpu=h2d / dt / 1e9, h2d_ceiling_gbs_per_gpu=ceiling,
+                frac_of_h2d_ceiling=h2d / dt / 1e9 / ceiling,
+                note="a streamed job: every step uploads its batch from pinned host buffers (chunked H2D on a "
+                     "copy stream overlapped with the fused engine); the per-group means are read back into "
+                     "pinned buffers once, at the end of the job, inside the timed region; the ceiling is the "
+                     "pinned H2D copy rate of a rank measured while all ranks copy at once (PCIe / host fabric)")
 
 
 def main():
@@ -462,6 +653,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the other BASELINE configurations (roofline.modes)")
+    ap.add_argument("--no-fixed-job", action="store_true", help="skip the fixed 1000-time job (sustained / strong scaling)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the check of the reduced sums against one rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = CONFIGS[args.config]
