@@ -53,17 +53,27 @@ def run_pipeline(a, wins, precision, noise, noise_in=None, thermal=True, seed=7,
 
 
 def check_against_oracle(res, ref, group_sizes, rtol, keys):
+    """Norm-wise over the delay row at the tolerance itself (measured at n = 310: 7e-7 in complex64,
+    tests/test_gpu_parity_hardening.py).  The no-autos mean is a difference of two sums and can be
+    arbitrarily small next to them (noise-like data), so its error is measured on the scale of the
+    all-pairs mean of the same quantity times n / (n - 1)."""
     for key in keys:
         for g, n in enumerate(group_sizes):
-            want = ref[key][g]
+            want = np.asarray(ref[key][g])
             if key.endswith("noautos") and n == 1:
+                assert np.all(np.isnan(res[key][g])), f"{key} group {g}: one baseline has no cross pairs"
                 continue
-            # the no-autos mean subtracts two sums that are ~n times larger
-            tol = rtol * (4 if key.endswith("_all") else 4 * max(n, 2))
             if key.startswith("thermal"):
-                np.testing.assert_allclose(res[key][g], want, rtol=tol, err_msg=f"{key} group {g}")
-            else:
-                assert_close(res[key][g], want, tol, what=f"{key} group {g} (n={n})")
+                np.testing.assert_allclose(res[key][g], want, rtol=4 * rtol, err_msg=f"{key} group {g}")
+                continue
+            got = np.asarray(res[key][g])
+            scale = np.abs(want).max(axis=-1, keepdims=True)
+            if key.endswith("noautos"):
+                all_ref = np.abs(np.asarray(ref[key.replace("noautos", "all")][g])).max(axis=-1, keepdims=True)
+                scale = np.maximum(scale, all_ref * n / (n - 1))
+            err = np.abs(got - want)
+            assert np.all(err <= rtol * scale), (
+                f"{key} group {g} (n={n}): max err/scale = {(err / scale).max():.3e} (rtol {rtol})")
 
 
 @pytest.mark.parametrize(
@@ -153,11 +163,12 @@ def test_fused_engine_large_group_and_many_items(cuda_device):
             X = orc.normalized_fourier_transform(x, 97656.25)
             s1 = X.sum(1)
             want_all = (np.abs(s1) ** 2).mean(1) / n**2
-            assert_close(res["power_all"][g, s], want_all, 4 * RTOL_C64, what=f"all g{g}")
+            assert_close(res["power_all"][g, s], want_all, RTOL_C64, what=f"all g{g}")
             if n > 1:
                 s2 = (np.abs(X) ** 2).sum(1)
                 want = ((np.abs(s1) ** 2 - s2) / (n * (n - 1))).mean(1)
-                assert_close(res["power_noautos"][g, s], want, 4 * n * RTOL_C64, what=f"noautos g{g}")
+                scale = np.maximum(np.abs(want).max(-1, keepdims=True), np.abs(want_all).max(-1, keepdims=True) * n / (n - 1))
+                assert np.all(np.abs(res["power_noautos"][g, s] - want) <= RTOL_C64 * scale), f"noautos g{g}"
 
 
 @pytest.mark.parametrize("wins,F0", [([(0, 202)], 203), ([(95, 115)], 203), ([(3, 66), (70, 133)], 160)])
