@@ -680,20 +680,24 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     if (blue_path) return run_engine_blue(pl.blue_m, P, legs, st, &g_last_launches);
     return run_engine_f32(N, P, legs, st, &g_last_launches);
   }
-  // complex128: data and thermal legs in fp64, one launch each (register budget); the noise
-  // realisation is fp32 in both modes and takes the packed engine
-  for (int leg = 1; leg <= 4 && rc == SDS_OK; leg <<= 1)
-    if (legs & leg) {
-      if ((rc = setup()) != SDS_OK) return rc;
-      if (leg == LEG_NOISE) {
-        EngineParams Pn = P;
-        Pn.taper = pl.taper_f;
-        Pn.tw = pl.team_tw_f;
-        rc = run_engine_f32(N, Pn, LEG_NOISE, st, &g_last_launches);
-      } else {
-        rc = run_engine<double>(N, P, leg, st);
-      }
-    }
+  // complex128: the data leg in fp64 (sds_engine.cu), then ONE launch of the packed engine for the
+  // noise realisation (fp32 in every mode) and the thermal sums in fp64 -- it stages nsample and the
+  // flags anyway and its fp64 pipe is idle: 9 + 5 = 14 bytes per sample in two launches (the first
+  // version took three: 9 + 5 + 4).  Thermal without noise keeps the fp64 thermal-only kernel.
+  if (legs & LEG_DATA) {
+    if ((rc = setup()) != SDS_OK) return rc;
+    if ((rc = run_engine<double>(N, P, LEG_DATA, st)) != SDS_OK) return rc;
+  }
+  if (legs & LEG_NOISE) {
+    if ((rc = setup()) != SDS_OK) return rc;
+    EngineParams Pn = P;
+    Pn.taper = pl.taper_f;
+    Pn.tw = pl.team_tw_f;
+    rc = run_engine_f32(N, Pn, LEG_NOISE | ((legs & LEG_THERMAL) ? LEG_THERMAL64 : 0), st, &g_last_launches);
+  } else if (legs & LEG_THERMAL) {
+    if ((rc = setup()) != SDS_OK) return rc;
+    rc = run_engine<double>(N, P, LEG_THERMAL, st);
+  }
   return rc;
 }
 

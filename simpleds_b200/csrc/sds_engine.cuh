@@ -10,6 +10,7 @@ constexpr int ENG_STAGES = 3;
 #define ENG_MINBLOCKS 1
 #endif
 constexpr int LEG_DATA = 1, LEG_NOISE = 2, LEG_THERMAL = 4;
+constexpr int LEG_THERMAL64 = 8;  // fp32 engine only: thermal sums in fp64 (complex128 mode)
 
 struct EngineParams {
   const float2 *vis;

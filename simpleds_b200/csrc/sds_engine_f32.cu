@@ -84,8 +84,11 @@ __global__ void __launch_bounds__(E3Cfg<N, LEGS, GAUSS>::THREADS, E3Cfg<N, LEGS,
 engine_f32_kernel(const __grid_constant__ EngineParams P) {
   // LEGS without LEG_DATA (the noise leg alone) serves the complex128 mode, whose data and
   // thermal legs run in fp64 (sds_engine.cu) while the noise realisation stays fp32
+  // LEG_THERMAL64: the thermal sums in fp64 (complex128 mode, where the thermal estimate must hold
+  // 1e-10: its sums ride in the noise launch, whose fp64 pipe is idle and which stages nsample anyway)
   constexpr bool HAS_D = (LEGS & LEG_DATA) != 0, HAS_N = (LEGS & LEG_NOISE) != 0,
-                 HAS_T = (LEGS & LEG_THERMAL) != 0;
+                 HAS_T = (LEGS & LEG_THERMAL) != 0, T64 = (LEGS & LEG_THERMAL64) != 0;
+  static_assert(!(HAS_T && T64), "thermal sums are fp32 or fp64, not both");
   using C = E3Cfg<N, LEGS, GAUSS>;
   using FFT = TeamFftX<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
@@ -214,6 +217,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // right neighbour, [0..2] left-end and [3..5] right-end deficits.
     f2 tA[4], tB[4], tC[4];
     float dfc[48];
+    double dA[8], dB[8], dC[8];  // T64: the same sums per channel tau + TPR r in fp64
+    double ddfc[T64 ? 48 : 1];
     bool dirty_time = false;
     double th_all_acc = 0.0, th_auto_acc = 0.0;
 #pragma unroll
@@ -223,6 +228,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dA[r] = dB[r] = dC[r] = 0.0;
 
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
@@ -241,7 +248,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
     // on the critical path of every row)
     float tint_next = 1.f;
-    if (HAS_N || HAS_T)
+    if (HAS_N || HAS_T || T64)
       tint_next = __ldg(P.int_time + it_off + (int64_t)((ROWS == 1 || sub < ng) ? sub : 0) * P.ntime);
     for (int step = 0; step < nsteps; ++step) {
       team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
@@ -250,7 +257,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
       const float tint = tint_next;
-      if ((HAS_N || HAS_T) && step + 1 < nsteps) {
+      if ((HAS_N || HAS_T || T64) && step + 1 < nsteps) {
         const bool wrap = ci0 + ROWS >= ng;
         const int ni = (wrap ? 0 : ci0 + ROWS) + sub;
         // lane_zero (= 0 at run time, but lane-dependent as far as ptxas can tell) keeps the address, and with it
@@ -272,7 +279,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       // a = nsample^-1/2 (0 where invalid): shared by the noise amplitude and the thermal sums
       float av[8];
       bool all_ok = true;
-      if (HAS_N || HAS_T) {
+      if (HAS_N || HAS_T || T64) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float nv = ns_s[TPR * r];
@@ -385,6 +392,41 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         }
       }
 
+      if (T64) {
+        // a = nsample^-1/2 in fp64: the fp32 approximation (2 ulp) and one Newton step (-> 1e-13)
+        const double itd = (tint > 0.f) ? 1.0 / (double)tint : 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const double nvd = (double)ns_s[TPR * r], y0 = (double)av[r];
+          const double a = y0 * fma(-0.5 * nvd * y0, y0, 1.5);  // av = 0 (invalid sample) stays 0
+          const double ab = a * itd;
+          dA[r] += a;
+          dB[r] += ab;
+          dC[r] = fma(a, ab, dC[r]);
+        }
+        if (team_any<TEAM>(active && !all_ok, bar_id)) {
+          if (!dirty_time) {
+#pragma unroll 1
+            for (int k = 0; k < 48; ++k) ddfc[k] = 0.0;
+            dirty_time = true;
+          }
+          if (active) {
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+              const int c = tau + TPR * q;
+              if (c + 1 >= N) continue;
+              const float nl = ns_s[TPR * q], nr = ns_s[TPR * q + 1];
+              if ((nl > 0.f) == (nr > 0.f)) continue;
+              const double a1 = rsqrt_t<double>(nl > 0.f ? nl : nr);
+              double *d = ddfc + 6 * q + (nl > 0.f ? 0 : 3);
+              d[0] += a1;
+              d[1] += a1 * itd;
+              d[2] += a1 * a1 * itd;
+            }
+          }
+        }
+      }
+
       // ---- advance the consumer; close the time when its last row is done -----------
       slot_c = slot_c + 1 == E3_STAGES ? 0 : slot_c + 1;
       if (slot_c == 0) par_c ^= 1u;
@@ -462,6 +504,53 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
           dirty_time = false;
         }
+        if (T64) {
+          const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N + tau;
+          const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N + tau;
+          // right neighbours' sums (channel + 1) through this row's first exchange buffer, one
+          // quantity per round (N doubles fill the buffer)
+          double Ap[8], Bp[8], Cp[8];
+#pragma unroll
+          for (int rnd = 0; rnd < 3; ++rnd) {
+            team_sync<TEAM>(bar_id);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const double v = rnd == 0 ? dA[r] : rnd == 1 ? dB[r] : dC[r];
+              asm volatile("st.shared.f64 [%0], %1;" ::"r"(xa + 8u * (uint32_t)(tau + TPR * r)), "d"(v) : "memory");
+            }
+            team_sync<TEAM>(bar_id);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              double v = 0.0;
+              if (r < 7 || tau + 1 < TPR)
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(xa + 8u * (uint32_t)(tau + TPR * r + 1)) : "memory");
+              if (rnd == 0) Ap[r] = v; else if (rnd == 1) Bp[r] = v; else Cp[r] = v;
+            }
+          }
+          if (dirty_time) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              dA[r] -= ddfc[6 * r + 0]; dB[r] -= ddfc[6 * r + 1]; dC[r] -= ddfc[6 * r + 2];
+              Ap[r] -= ddfc[6 * r + 3]; Bp[r] -= ddfc[6 * r + 4]; Cp[r] -= ddfc[6 * r + 5];
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            double a = dA[r], b = dB[r], ap = Ap[r], bp = Bp[r];
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, off);
+              b += __shfl_xor_sync(0xffffffffu, b, off);
+              ap += __shfl_xor_sync(0xffffffffu, ap, off);
+              bp += __shfl_xor_sync(0xffffffffu, bp, off);
+            }
+            const double l = __ldg(wlp + TPR * r), rr = __ldg(wrp + TPR * r);
+            if (sub == 0) th_all_acc += l * a * b + rr * ap * bp;
+            th_auto_acc += l * dC[r] + rr * Cp[r];
+            dA[r] = dB[r] = dC[r] = 0.0;
+          }
+          dirty_time = false;
+        }
       }
     }
 
@@ -488,7 +577,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         }
       }
     }
-    if (HAS_T) {
+    if (HAS_T || T64) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         th_all_acc += __shfl_xor_sync(0xffffffffu, th_all_acc, off);
@@ -536,6 +625,7 @@ template <int N>
 static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *launches) {
   if (P.noise_mode == 1 && P.noise_gauss) {
     switch (legs) {
+      case LEG_NOISE | LEG_THERMAL64: return launch_f32<N, LEG_NOISE | LEG_THERMAL64, true>(P, st, launches);
       case 2: return launch_f32<N, 2, true>(P, st, launches);
       case 3: return launch_f32<N, 3, true>(P, st, launches);
       case 7: return launch_f32<N, 7, true>(P, st, launches);
@@ -544,6 +634,7 @@ static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *laun
   }
   switch (legs) {
     case 1: return launch_f32<N, 1>(P, st, launches);
+    case LEG_NOISE | LEG_THERMAL64: return launch_f32<N, LEG_NOISE | LEG_THERMAL64>(P, st, launches);
     case 2: return launch_f32<N, 2>(P, st, launches);
     case 3: return launch_f32<N, 3>(P, st, launches);
     case 5: return launch_f32<N, 5>(P, st, launches);
