@@ -506,7 +506,9 @@ class DelaySpectrum:
             setattr(this, attr, ops.take_windows(getattr(this, attr), freq_chans))
         this.Nspws, this.Nfreqs = int(nspws), int(num_freqs[0])
         this._set_delay_array()
-        this.power_array = this.noise_power = this.thermal_power = None
+        # like the reference (ds.py:3306-3308): redshift, k_parallel and k_perpendicular exist right
+        # after a window selection; the power arrays are left alone
+        this.update_cosmology()
         if not inplace:
             return this
 

@@ -63,6 +63,22 @@ dimensionless_unscaled = Unit("")
 Jy, Hz, K, sr, s, ns, m, mK = (Unit(u) for u in ("Jy", "Hz", "K", "sr", "s", "ns", "m", "mK"))
 
 
+# scale of the prefixed / non-SI unit names the path meets, to the SI base the reference converts to
+# with ``.si`` (utils.py:560, 564); a unit made of other names has scale 1
+SI_SCALE = {"ns": (1e-9, "s"), "us": (1e-6, "s"), "ms": (1e-3, "s"), "kHz": (1e3, "Hz"), "MHz": (1e6, "Hz"),
+            "GHz": (1e9, "Hz"), "mK": (1e-3, "K"), "km": (1e3, "m"), "Mpc": (3.085677581491367e22, "m")}
+
+
+def to_si(unit):
+    """(scale, SI unit) of a unit tag: value_SI = value * scale  (astropy's ``Quantity.si``)."""
+    scale, out = 1.0, {}
+    for name, power in Unit(unit)._p.items():
+        f, base = SI_SCALE.get(name, (1.0, name))
+        scale *= f ** float(power)
+        out[base] = out.get(base, Fraction(0)) + power
+    return scale, Unit(out)
+
+
 class UnitConversionError(ValueError):
     """Mirrors astropy.units.UnitConversionError (a ValueError subclass there too)."""
 

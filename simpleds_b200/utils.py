@@ -8,7 +8,7 @@ import torch
 from scipy.signal import windows
 
 from . import ops
-from .units import Quantity, Unit, is_quantity
+from .units import Quantity, Unit, is_quantity, to_si
 
 C_M_PER_S = 299792458.0  # astropy.constants.c
 K_B_J_PER_K = 1.380649e-23  # astropy.constants.k_B
@@ -67,9 +67,12 @@ def normalized_fourier_transform(
     t = _to_device(value, complex_=True)
     n = t.shape[-1]
     plan = ops.get_plan(n, ops.math_of(t.dtype), taper)
-    dx = float(np.asarray(delta_x.value))
+    # the reference multiplies by delta_x.si (utils.py:560, 564): a step given in MHz or ns scales
+    # the result like the same step in Hz or s, and the output carries the SI unit
+    si_scale, si_unit = to_si(delta_x.unit)
+    dx = float(np.asarray(delta_x.value)) * si_scale
     out = ops.delay_transform(plan, t, None, dx, inverse=inverse)
-    return _wrap(out, unit * delta_x.unit, was_numpy, True)
+    return _wrap(out, unit * si_unit, was_numpy, True)
 
 
 def cross_multiply_array(array_1, array_2=None, axis=0):

@@ -59,6 +59,12 @@ def test_ft_kats_and_units(cuda_device, golden):
     assert out.unit == Unit("m Hz")  # t_utils.py:415-423
     with pytest.raises(ValueError):  # reference quirk: last axis only
         utils.normalized_fourier_transform(np.zeros((4, 21, 3)), _q(2.5), axis=1)
+    # the reference multiplies by delta_x.si (utils.py:560): 0.5 MHz is 5e5 Hz, 4 ns is 4e-9 s
+    hz = utils.normalized_fourier_transform(_q(fake, "Jy"), _q(5e5, "Hz"), axis=3)
+    mhz = utils.normalized_fourier_transform(_q(fake, "Jy"), _q(0.5, "MHz"), axis=3)
+    assert mhz.unit == Unit("Jy Hz") and np.allclose(mhz.numpy(), hz.numpy(), rtol=1e-14, atol=0)
+    nsec = utils.normalized_fourier_transform(_q(fake, "Jy"), _q(4.0, "ns"), axis=3)
+    assert nsec.unit == Unit("Jy s") and np.allclose(nsec.numpy(), hz.numpy() * (4e-9 / 5e5), rtol=1e-13, atol=0)
 
 
 @pytest.mark.parametrize("n,f0", [(21, 21), (10, 21), (64, 203), (256, 1024), (203, 203), (128, 512),
@@ -289,6 +295,9 @@ def test_select_spectral_windows_errors_and_copy(cuda_device):
         ds.select_spectral_windows([(0, 5), (6, 13)])
     new = ds.select_spectral_windows([(1, 10)], inplace=False)
     assert new.Nfreqs == 10 and ds.Nfreqs == 21 and new.data_array.shape[-1] == 10
+    # like the reference (ds.py:3306): the cosmological axes exist right after the selection
+    assert new.redshift is not None and new.k_parallel is not None
+    assert np.asarray(new.redshift).shape == (1,) and tuple(np.asarray(new.k_parallel.value).shape) == (1, 10)
     assert np.array_equal(new.data_array.numpy()[0], pr["vis"][0][..., 1:11].astype(complex))
     byfreq = ds.select_spectral_windows(freqs=pr["freq_array_hz"][:, 3:9], inplace=False)
     assert np.array_equal(byfreq.freq_array.value, pr["freq_array_hz"][:, 3:9])
