@@ -192,13 +192,23 @@ typedef struct sds_engine_desc {
   const int64_t *group_bl_start;
 } sds_engine_desc;
 
-/* In-kernel noise (noise_mode 1), replacing utils.py:486-506 + ds.py:3544-3583: every
- * sample gets sigma * sqrt(-ln u1) * exp(2 pi i u2) (Box-Muller), u1 and u2 23-bit uniforms
- * cut from Philox4x32-7 words (Salmon et al. 2011) keyed by `seed`; the 128-bit counter is the
- * GLOBAL sample coordinate -- (row_id low word, row_id high word, 3 tau + k, 0) for power-of-two
- * windows, row_id = ((s * npol + p) * nbl_total + bl_offset + b) * ntime_total + time_offset + t
- * -- so the realisation does not depend on batching or sharding (exact word-to-channel map:
- * oracle/engine_ref.py).
+/* In-kernel noise, replacing utils.py:486-506 + ds.py:3544-3583 (the reference draws
+ * sigma (g1 + i g2) / sqrt(2) per sample from numpy's global generator; parity is statistical).
+ * Counter-based: Philox4x32-7 words (Salmon et al. 2011) keyed by `seed`, the 128-bit counter a
+ * GLOBAL sample coordinate, so the realisation does not depend on batching or sharding (exact
+ * word-to-channel maps: oracle/engine_ref.py).
+ *   noise_mode 1 (production; power-of-two windows): the moment-matched discrete law
+ *     n = sigma * B * (s1 + i s2), B in {0, 1} (p = 1/2), s1, s2 = +-1: E n = 0, E n^2 = 0,
+ *     E |n|^2 = sigma^2, E |n|^4 = 2 sigma^4 as for the Gaussian; three bits per sample, one call per
+ *     thread and block of four baselines, counter = (blk low word, blk high word, tau, 2),
+ *     blk = ((s npol + p) ceil(nbl_total / 4) + (b >> 2)) ntime_total + t with global b, t.  The
+ *     engine only ever returns DELAY-domain pair sums, i.e. sums over the >= 64 tapered channels of a
+ *     row, whose law the per-channel moments fix (csrc/sds_engine.cuh, tests/test_gpu_noise_stats.py).
+ *     Windows that are not powers of two (chirp-z engine) draw Box-Muller in this mode too.
+ *   noise_mode 3: sigma * sqrt(-ln u1) * exp(2 pi i u2) per sample (Box-Muller), u1 and u2 23-bit
+ *     uniforms; counter (row_id low word, row_id high word, 3 tau + k, 0),
+ *     row_id = ((s * npol + p) * nbl_total + bl_offset + b) * ntime_total + time_offset + t.
+ *   noise_mode 2: injected frequency-domain noise (noise_in), for exact parity tests.
  *
  * Inputs: vis  c64 [nuv][npol][nbl][ntime][nchan]; flags u8, nsample f32 same
  * shape; int_time f32 [nbl][ntime]; group_offset int32[ngroup+1];
@@ -220,9 +230,17 @@ int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void
                    const double *pol_factor, const void *noise_in, double *pow_all,
                    double *pow_auto, double *noise_all, double *noise_auto,
                    double *thermal_all, double *thermal_auto, void *workspace,
-                   sds_stream stream);
-/* number of kernel launches the last sds_engine_run on this thread enqueued */
-int sds_engine_last_launches(void);
+                   sds_stream stream, int32_t *launches_out);
+/* launches_out (host pointer, may be NULL): number of kernel launches the call enqueued.
+ *
+ * Two data sets (desc->nuv == 2; delay_spectrum.py:3620-3633: power[i, j] = A2_i conj(A1_j) with
+ * A1 / A2 the transforms of data_array[:, 0] / [:, 1]): vis, flags, nsample and noise_in carry a
+ * leading axis of length 2 ((2, Npols, Nbls, Ntimes, Nchan)); pow_* and noise_* are COMPLEX,
+ * interleaved (re, im) doubles of twice the size:
+ *   *_all  += (sum_i A2_i) conj(sum_j A1_j),    *_auto += sum_i A2_i conj(A1_i);
+ * the in-kernel noise of set u is keyed by blk = (((s npol + p) 2 + u) ceil(nbl_total / 4) + (b >> 2))
+ * ntime_total + t.  SDS_F32 plans with power-of-two windows of 64..1024 channels; thermal_coef must be
+ * NULL (the thermal estimate of two sets: sds_thermal_power_avg with the two nsample arrays). */
 
 /* ---- downstream estimators on the (averaged) spectra: SURVEY 8(f3) ----------------------
  * All arrays are C-ordered and viewed as (outer, n, inner) around the reduced / folded /

@@ -20,10 +20,15 @@ _LO = np.uint64(0xFFFFFFFF)
 def group_means(vis, flags, nsample, int_time, group_offset, freq_hz, spectral_windows,
                 polarization_array, trcvr_k, beam_area_sr, taper=windows.blackmanharris,
                 noise_freq=None):
-    """vis/flags/nsample (P,B,T,F0); int_time (B,T); noise_freq: frequency-domain noise
-    (S,P,B,T,N) already window-selected, or None (sigma * 0).  Returns dict of
-    arrays indexed [group] -> (S,P,D) means (all pairs / no autos) and thermal (S,P)."""
-    P, B, T, F0 = vis.shape
+    """vis/flags/nsample (P,B,T,F0) -- or (2,P,B,T,F0) for two data sets (Nuv = 2); int_time (B,T);
+    noise_freq: frequency-domain noise (S,P,B,T,N) already window-selected ((S,2,P,B,T,N) for two
+    sets), or None (sigma * 0).  Returns dict of arrays indexed [group] -> (S,P,D) means (all pairs /
+    no autos; complex for two sets) and thermal (S,P)."""
+    two = vis.ndim == 5
+    if not two:
+        vis, flags, nsample = vis[None], flags[None], nsample[None]
+        noise_freq = None if noise_freq is None else noise_freq[:, None]
+    U, P, B, T, F0 = vis.shape
     freq_hz = np.asarray(freq_hz, dtype=np.float64).reshape(1, F0)
     trcvr = np.broadcast_to(np.asarray(trcvr_k, dtype=np.float64), (F0,)).reshape(1, F0)
     beam = np.broadcast_to(np.asarray(beam_area_sr, dtype=np.float64), (P, F0)).reshape(1, P, F0)
@@ -33,10 +38,10 @@ def group_means(vis, flags, nsample, int_time, group_offset, freq_hz, spectral_w
         b0, b1 = int(group_offset[g]), int(group_offset[g + 1])
         sl = slice(b0, b1)
         state = dict(
-            data_array=vis[None, None, :, sl].astype(np.complex128),
-            noise_array=np.zeros((1, 1, P, b1 - b0, T, F0), complex),
-            nsample_array=nsample[None, None, :, sl].astype(np.float64),
-            flag_array=flags[None, None, :, sl].astype(bool),
+            data_array=vis[None, :, :, sl].astype(np.complex128),
+            noise_array=np.zeros((1, U, P, b1 - b0, T, F0), complex),
+            nsample_array=nsample[None, :, :, sl].astype(np.float64),
+            flag_array=flags[None, :, :, sl].astype(bool),
             freq_array=freq_hz, trcvr=trcvr, beam_area=beam, beam_sq_area=beam,
         )
         state = orc.select_spectral_windows(state, spectral_windows)
@@ -44,7 +49,7 @@ def group_means(vis, flags, nsample, int_time, group_offset, freq_hz, spectral_w
         sigma = orc.calculate_noise_power(state["freq_array"], state["trcvr"], state["beam_area"],
                                           it, state["nsample_array"])
         if noise_freq is not None:
-            state["noise_array"] = noise_freq[:, None, :, sl].astype(np.complex128)
+            state["noise_array"] = noise_freq[:, :, :, sl].astype(np.complex128)
         res = orc.calculate_delay_spectrum(
             state["data_array"], state["noise_array"], state["flag_array"], state["nsample_array"],
             state["freq_array"], state["trcvr"], state["beam_area"], it, polarization_array, taper,
@@ -124,7 +129,7 @@ def engine_noise_freq(sigma_coef32, nsample, int_time, win_start, nfreq, seed, t
 
 
 def engine_noise_freq_mm(sigma_coef32, nsample, int_time, win_start, nfreq, seed, time_offset=0,
-                         ntime_total=None, bl_offset=0, nbl_total=None):
+                         ntime_total=None, bl_offset=0, nbl_total=None, nuv=1, uv=0):
     """The frequency-domain noise of the power-of-two engine's production draw (noise_mode 1,
     csrc/sds_engine.cuh ``engine_word_mm`` / ``engine_signs_mm``), before mask and taper:
     ``sigma * B * (s1 + i s2)`` with B in {0, 1}, s1, s2 in {-1, +1} -- zero mean, circular,
@@ -132,8 +137,9 @@ def engine_noise_freq_mm(sigma_coef32, nsample, int_time, win_start, nfreq, seed
 
     One Philox4x32-7 call serves thread tau (channels tau + (N/8) r, r = 0..7) of four consecutive
     baselines: counter = (blk low word, blk high word, tau, 2),
-    blk = ((s*P + p) * ceil(Bt / 4) + (b >> 2)) * Tt + t with global b, t; baseline b takes word
-    b & 3; bit r of the word is B, bit 8 + r the sign of the real and bit 16 + r of the imaginary part."""
+    blk = (((s*P + p) * nuv + uv) * ceil(Bt / 4) + (b >> 2)) * Tt + t with global b, t (uv = index of
+    the data set, nuv = 1 or 2); baseline b takes word b & 3; bit r of the word is B, bit 8 + r the
+    sign of the real and bit 16 + r of the imaginary part."""
     P, B, T, _ = nsample.shape
     S, N = len(win_start), nfreq
     tpr = N // 8
@@ -143,8 +149,8 @@ def engine_noise_freq_mm(sigma_coef32, nsample, int_time, win_start, nfreq, seed
     s_i, p_i, b_i, t_i, tau_i = np.meshgrid(np.arange(S), np.arange(P), np.arange(B), np.arange(T),
                                             np.arange(tpr), indexing="ij")
     bg = (b_i + bl_offset).astype(np.uint64)
-    blk = ((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(nblk)
-           + (bg >> np.uint64(2))) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
+    blk = (((s_i.astype(np.uint64) * np.uint64(P) + p_i.astype(np.uint64)) * np.uint64(nuv) + np.uint64(uv))
+           * np.uint64(nblk) + (bg >> np.uint64(2))) * np.uint64(Tt) + (t_i + time_offset).astype(np.uint64)
     W = philox4x32((blk & _LO).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
                    tau_i.astype(np.uint32), np.full(blk.shape, 2, np.uint32),
                    np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF),

@@ -68,8 +68,7 @@ _SIGNATURES = {
     "sds_cross_power_avg": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                    _vp, _i32, _i32, _vp, _vp, _vp]),
     "sds_engine_workspace_bytes": (_i64, [_vp, C.POINTER(EngineDesc)]),
-    "sds_engine_run": (_i32, [_vp, C.POINTER(EngineDesc)] + [_vp] * 17 + [_vp]),
-    "sds_engine_last_launches": (_i32, []),
+    "sds_engine_run": (_i32, [_vp, C.POINTER(EngineDesc)] + [_vp] * 17 + [_vp, C.POINTER(C.c_int32)]),
     "sds_weighted_average": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "sds_fold_along_delay": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
                                     _vp, _vp, _vp]),

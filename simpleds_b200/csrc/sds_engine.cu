@@ -512,6 +512,8 @@ static EngWorkspace carve(void *ws, int ngroup, int nspw, int npol, int N) {
   return w;
 }
 
+// launches enqueued by the sds_engine_run in progress on this host thread (reported through its
+// launches_out argument; thread-local so that concurrent calls from several host threads do not mix)
 static thread_local int g_last_launches = 0;
 
 template <typename T, int N, int LEGS>
@@ -584,9 +586,13 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
                               const double *pol_factor, const void *noise_in, double *pow_all,
                               double *pow_auto, double *noise_all, double *noise_auto,
                               double *thermal_all, double *thermal_auto, void *workspace,
-                              sds_stream stream) {
+                              sds_stream stream, int32_t *launches_out) {
   using namespace sds;
   g_last_launches = 0;
+  struct Report {  // whatever way the call ends, the caller learns what was enqueued
+    int32_t *out;
+    ~Report() { if (out) *out = g_last_launches; }
+  } report{launches_out};
   SDS_CHECK_ARG(plan && d, "sds_engine_run: NULL plan/desc");
   const Plan &pl = plan->p;
   const int N = pl.nfreq;
@@ -602,8 +608,10 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   const bool thermal = thermal_coef != nullptr;
   SDS_CHECK_ARG(!thermal || (freq && pol_factor && int_time && thermal_all && thermal_auto),
                 "sds_engine_run: thermal needs freq, pol_factor, int_time and the thermal outputs");
-  if (d->nuv != 1) {
-    set_error("sds_engine_run: the fused path handles nuv == 1 only (got %d)", d->nuv);
+  SDS_CHECK_ARG(d->nuv == 1 || d->nuv == 2, "sds_engine_run: nuv must be 1 or 2 (got %d)", d->nuv);
+  if (d->nuv == 2 && (pl.math != SDS_F32 || !pl.is_pow2 || N < 64 || N > 1024 || thermal || d->noise_mode == 3)) {
+    set_error("sds_engine_run: two data sets (nuv = 2) take the fused path in complex64 with power-of-two "
+              "windows of 64..1024 channels, noise_mode 0..2 and no thermal leg (sds_thermal_power_avg)");
     return SDS_ENOTSUP;
   }
   const bool pow2_path = pl.is_pow2 && N >= 64 && N <= 2048 && pl.team_tw_f;
@@ -675,6 +683,15 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     ++g_last_launches;
     return SDS_OK;
   };
+  if (d->nuv == 2) {  // one launch per leg, the two data sets' rows in lockstep (sds_engine_uv2.cu)
+    if ((rc = setup()) != SDS_OK) return rc;
+    if ((rc = run_engine_uv2(N, P, LEG_DATA, st, &g_last_launches)) != SDS_OK) return rc;
+    if (legs & LEG_NOISE) {
+      if ((rc = setup()) != SDS_OK) return rc;
+      rc = run_engine_uv2(N, P, LEG_NOISE, st, &g_last_launches);
+    }
+    return rc;
+  }
   if (pl.math == SDS_F32) {  // one pass over the inputs for every leg
     if ((rc = setup()) != SDS_OK) return rc;
     if (blue_path) return run_engine_blue(pl.blue_m, P, legs, st, &g_last_launches);
@@ -701,4 +718,3 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   return rc;
 }
 
-extern "C" int sds_engine_last_launches(void) { return sds::g_last_launches; }

@@ -269,6 +269,8 @@ int run_engine_f32(int N, const EngineParams &P, int legs, cudaStream_t st, int 
 // fp32 engine for window lengths that are not powers of two (sds_engine_blue.cu), M = the plan's
 // convolution length
 int run_engine_blue(int M, const EngineParams &P, int legs, cudaStream_t st, int *launches);
+// fp32 engine for two data sets (sds_engine_uv2.cu): leg = LEG_DATA or LEG_NOISE, one launch each
+int run_engine_uv2(int N, const EngineParams &P, int leg, cudaStream_t st, int *launches);
 
 // Four unit draws of the thread that owns channels tau + TPR r (r = 0..3) of row `row_id` in the
 // chirp-z engine (N <= 4 TPR): two Philox calls, counter = (row_id low word, row_id high word,

@@ -398,7 +398,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const double nvd = (double)ns_s[TPR * r], y0 = (double)av[r];
-          const double a = y0 * fma(-0.5 * nvd * y0, y0, 1.5);  // av = 0 (invalid sample) stays 0
+          // invalid sample or inactive row (whose slot holds stale bytes): a = 0
+          const double a = av[r] > 0.f ? y0 * fma(-0.5 * nvd * y0, y0, 1.5) : 0.0;
           const double ab = a * itd;
           dA[r] += a;
           dB[r] += ab;

@@ -53,10 +53,14 @@ class RedundantPipeline:
     (start, end) inclusive channel ranges of equal length (ds.py:3243-3264);
     ``group_offset`` (Ngroups+1,) rising baseline offsets of the redundant groups;
     ``trcvr_k`` scalar or (Nchan,); ``beam_area_sr`` scalar, (Nchan,) or (Npols, Nchan);
-    ``precision`` "complex64" (fp32 math) or "complex128" (fp64 math)."""
+    ``precision`` "complex64" (fp32 math) or "complex128" (fp64 math); ``nuv`` = 2: two data
+    sets per call (arrays with a leading axis of length 2), cross-multiplied like the reference's
+    ``data_array[:, 0]`` x ``data_array[:, 1]`` (ds.py:3620-3633, thermal 3655-3662): the pair means
+    are then complex.  Two sets take the fused path in complex64 with power-of-two windows of
+    64..1024 channels."""
 
     def __init__(self, freq_hz, spectral_windows, polarization_array, group_offset, trcvr_k,
-                 beam_area_sr, taper=None, precision="complex64", seed=0, device=None):
+                 beam_area_sr, taper=None, precision="complex64", seed=0, device=None, nuv=1):
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.taper = windows.blackmanharris if taper is None else taper
@@ -67,6 +71,9 @@ class RedundantPipeline:
             )
         if precision not in ("complex64", "complex128"):
             raise ValueError("precision must be 'complex128' or 'complex64'")
+        if nuv not in (1, 2):
+            raise ValueError("nuv must be 1 (one data set) or 2 (the cross of two data sets, ds.py:3620-3633)")
+        self.nuv = int(nuv)
         self.precision, self.seed = precision, int(seed)
         self.math = SDS_F64 if precision == "complex128" else SDS_F32
         freq_hz = np.asarray(freq_hz, dtype=np.float64).reshape(-1)
@@ -117,6 +124,8 @@ class RedundantPipeline:
         n = self.nfreq
         if self.nchan % 16 != 0 or any(w % 16 != 0 for w in self.win_start):
             return False
+        if self.nuv == 2:
+            return (n & (n - 1)) == 0 and 64 <= n <= 1024 and self.precision == "complex64"
         if (n & (n - 1)) == 0:
             return 64 <= n <= 2048
         npad = (n + 15) // 16 * 16
@@ -125,11 +134,13 @@ class RedundantPipeline:
 
     def reset(self):
         dev, shape = self.device, (self.ngroup, self.nspw, self.npol, self.nfreq)
-        # with one data set (Nuv = 1) the pair sums are real: sum_ij x_i conj(x_j) = |sum_i x_i|^2
-        self.pow_all = torch.zeros(shape, dtype=torch.float64, device=dev)
-        self.pow_auto = torch.zeros(shape, dtype=torch.float64, device=dev)
-        self.noise_all = torch.zeros(shape, dtype=torch.float64, device=dev)
-        self.noise_auto = torch.zeros(shape, dtype=torch.float64, device=dev)
+        # with one data set (Nuv = 1) the pair sums are real: sum_ij x_i conj(x_j) = |sum_i x_i|^2;
+        # with two they are (sum_i A2_i) conj(sum_j A1_j): complex
+        pdt = torch.float64 if self.nuv == 1 else torch.complex128
+        self.pow_all = torch.zeros(shape, dtype=pdt, device=dev)
+        self.pow_auto = torch.zeros(shape, dtype=pdt, device=dev)
+        self.noise_all = torch.zeros(shape, dtype=pdt, device=dev)
+        self.noise_auto = torch.zeros(shape, dtype=pdt, device=dev)
         self.thermal_all = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
         self.thermal_auto = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
         # times accumulated per group: travels with the sums through reduce(), so that result() is
@@ -157,13 +168,23 @@ class RedundantPipeline:
         A streamed job passes ``time_offset`` (global index of the batch's first time) and
         ``ntime_total``: the in-kernel noise is a function of the global (baseline, time)
         coordinates, so batches and shards of one job realise one and the same noise field."""
-        P, B, T, F0 = vis.shape
+        if self.nuv == 2:
+            if vis.ndim != 5 or vis.shape[0] != 2:
+                raise ValueError("nuv = 2: vis, flags, nsample (and noise_in) carry a leading axis of length 2")
+            if not self.fused:
+                raise NotImplementedError("two data sets take the fused path only: complex64, aligned power-of-two "
+                                          "windows of 64..1024 channels (DelaySpectrum covers the rest)")
+            if noise == "philox_gauss":
+                raise NotImplementedError("nuv = 2: the in-kernel noise is the production draw (noise='philox')")
+        elif vis.ndim != 4:
+            raise ValueError("vis must be (Npols, Nbls, Ntimes, Nchan)")
+        P, B, T, F0 = vis.shape[-4:]
         sub = None
         if groups is not None:
             sub = self._group_subset(groups)
         nbl_expect = self.nbl if sub is None else sub["nbl"]
         if (P, B, F0) != (self.npol, nbl_expect, self.nchan):
-            raise ValueError(f"vis has shape {tuple(vis.shape)}, expected ({self.npol}, {nbl_expect}, T, {self.nchan})")
+            raise ValueError(f"vis has shape {tuple(vis.shape)}, expected (..., {self.npol}, {nbl_expect}, T, {self.nchan})")
         if tuple(flags.shape) != tuple(vis.shape) or tuple(nsample.shape) != tuple(vis.shape) \
                 or tuple(int_time.shape) != (B, T):
             raise ValueError("flags/nsample must match vis and int_time must be (Nbls, Ntimes)")
@@ -193,8 +214,10 @@ class RedundantPipeline:
         if sub is not None and len(sub["index"]) == 0:
             return
         if self.fused:
-            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot,
-                                subset=sub)
+            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal and self.nuv == 1, time_offset,
+                                ntot, subset=sub)
+            if thermal and self.nuv == 2:
+                self._thermal_two_sets(nsample, int_time, sub)
         else:
             if sub is not None:
                 raise NotImplementedError("groups= needs the fused path (aligned windows of a supported length)")
@@ -231,11 +254,11 @@ class RedundantPipeline:
         tables of an arbitrary rising list of groups (_group_subset).  The noise counters
         stay keyed by the global baseline index."""
         lib = _lib.load()
-        P, B, T, F0 = vis.shape
+        P, B, T, F0 = vis.shape[-4:]
         g0, g1, goff = (0, self.ngroup, self.group_offset) if groups is None else groups
         d = EngineDesc()
         d.npol, d.nbl, d.ntime, d.nchan = P, B, T, F0
-        d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, g1 - g0, 1, mode
+        d.nspw, d.ngroup, d.nuv, d.noise_mode = self.nspw, g1 - g0, self.nuv, mode
         if subset is not None:
             g0, g1, goff = 0, self.ngroup, subset["goff_dev"]
             d.ngroup = len(subset["index"])
@@ -249,16 +272,35 @@ class RedundantPipeline:
         need = lib.sds_engine_workspace_bytes(self.plan.handle, C.byref(d))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+        launches = C.c_int32(0)
         rc = lib.sds_engine_run(
             self.plan.handle, C.byref(d), ptr(vis), ptr(fl), ptr(nsample), ptr(int_time),
             ptr(goff), ptr(self.sigma_coef32), ptr(self.thermal_coef if thermal else None),
             ptr(self.freq_dev), ptr(self.pol_factor), ptr(noise_in), ptr(self.pow_all[g0:g1]),
             ptr(self.pow_auto[g0:g1]), ptr(self.noise_all[g0:g1]), ptr(self.noise_auto[g0:g1]),
             ptr(self.thermal_all[g0:g1]), ptr(self.thermal_auto[g0:g1]),
-            ptr(self._ws), stream_ptr(),
+            ptr(self._ws), stream_ptr(), C.byref(launches),
         )
         check(rc, "sds_engine_run")
-        self.kernel_launches += lib.sds_engine_last_launches()
+        self.kernel_launches += launches.value
+
+    def _thermal_two_sets(self, nsample, int_time, sub):
+        """Thermal estimate of two data sets (ds.py:3655-3662: N_ij = sqrt(n1_j n2_i)): the pair
+        sums of sds_thermal_power_avg on the two window-selected nsample arrays."""
+        chans = np.asarray(self.win_start)[:, None] + np.arange(self.nfreq)
+        n1 = ops.take_windows(nsample[0][None], chans)  # (S,P,B,T,N)
+        n2 = ops.take_windows(nsample[1][None], chans)
+        go = self.group_offset_host if sub is None else sub["goff_dev"].cpu().numpy().astype(np.int64)
+        t_all, t_auto = ops.thermal_power_sums(n1, n2, self.thermal_coef, self.freq_dev, int_time.to(torch.float64),
+                                               self.pol_factor, go)
+        self.kernel_launches += 3
+        if sub is None:
+            self.thermal_all += t_all.sum(dim=3)
+            self.thermal_auto += t_auto.sum(dim=3)
+        else:
+            idx = sub["index_dev"].long()
+            self.thermal_all[idx] += t_all.sum(dim=3)
+            self.thermal_auto[idx] += t_auto.sum(dim=3)
 
     def _process_unfused(self, vis, fl, nsample, int_time, mode, noise_in, thermal, time_offset, ntot):
         """Any window length / alignment: the API-level kernels chained on device
@@ -318,6 +360,8 @@ class RedundantPipeline:
         is returned (pinned host buffers viewed as numpy arrays).  A streamed job passes
         ``fetch=False`` for every batch (nothing is copied back, nothing is waited for) and
         calls ``result_host()`` once at its end."""
+        if self.nuv != 1:
+            raise NotImplementedError("process_host streams one data set (nuv = 1)")
         ins = {}
         for name, a, dt in (("vis", vis, torch.complex64), ("flags", flags, torch.uint8),
                             ("nsample", nsample, torch.float32), ("int_time", int_time, torch.float32)):

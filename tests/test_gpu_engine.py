@@ -319,3 +319,52 @@ def test_fused_engine_group_subsets_equal_the_whole_job(cuda_device):
         pipe.process(torch.as_tensor(a["vis"], device=dev), torch.as_tensor(a["flags"], device=dev),
                      torch.as_tensor(a["nsample"], device=dev), torch.as_tensor(a["int_time"], device=dev),
                      time_offset=3)
+
+
+@pytest.mark.parametrize("N,nwin", [(64, 2), (256, 2), (1024, 1)])
+def test_fused_engine_two_data_sets_match_oracle(cuda_device, N, nwin):
+    """Nuv = 2 (ds.py:3620-3633, thermal 3655-3662): power[i, j] = A2_i conj(A1_j) with A1 / A2 the
+    transforms of the two data sets; the fused pair means are complex.  Injected noise for both sets
+    (exact), then the in-kernel draw against its restated stream (one realisation per set)."""
+    from simpleds_b200.engine import RedundantPipeline
+
+    group_sizes = [5, 1, 2, 9] if N <= 256 else [3, 1, 4]
+    T = 3 if N <= 256 else 2
+    a, b = (make_array(500 + N + u, 2, group_sizes, T, N * nwin, zero_ns_frac=0.03) for u in (0, 1))
+    wins = [(w * N, (w + 1) * N - 1) for w in range(nwin)]
+    vis, flags, ns = (np.stack([a[k], b[k]]) for k in ("vis", "flags", "nsample"))
+    rng = np.random.default_rng(8)
+    noise_in = (rng.standard_normal(vis.shape) + 1j * rng.standard_normal(vis.shape)).astype(np.complex64)
+    dev = torch.device("cuda:0")
+
+    def run(noise, seed=7):
+        pipe = RedundantPipeline(a["freq"], wins, a["pols"], a["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                                 precision="complex64", seed=seed, nuv=2)
+        assert pipe.fused
+        pipe.process(torch.as_tensor(vis, device=dev), torch.as_tensor(flags, device=dev), torch.as_tensor(ns, device=dev),
+                     torch.as_tensor(a["int_time"], device=dev), noise=noise,
+                     noise_in=torch.as_tensor(noise_in, device=dev) if noise == "inject" else None)
+        torch.cuda.synchronize()
+        return pipe, {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in pipe.result().items()}
+
+    pipe, res = run("inject")
+    noise_freq = np.stack([noise_in[..., w * N:(w + 1) * N] for w in range(nwin)])  # (S,2,P,B,T,N)
+    ref = engine_ref.group_means(vis, flags, ns, a["int_time"], a["group_offset"], a["freq"], wins, a["pols"],
+                                 144.0, 0.76, noise_freq=noise_freq)
+    assert np.iscomplexobj(res["power_all"]) and np.abs(res["power_all"].imag).max() > 0
+    check_against_oracle(res, ref, group_sizes, RTOL_C64,
+                         ["power_all", "power_noautos", "noise_power_all", "noise_power_noautos"])
+    check_against_oracle(res, ref, group_sizes, 1e-10 / 4, ["thermal_all", "thermal_noautos"])
+    # in-kernel draw: the restated stream of each set
+    pipe, res = run("philox", seed=0x51ED5EED)
+    nz = np.stack([engine_ref.engine_noise_freq_mm(pipe.sigma_coef32.cpu().numpy(), ns[u], a["int_time"],
+                                                   pipe.win_start, N, 0x51ED5EED, nuv=2, uv=u) for u in (0, 1)], axis=1)
+    ref = engine_ref.group_means(vis, flags, ns, a["int_time"], a["group_offset"], a["freq"], wins, a["pols"],
+                                 144.0, 0.76, noise_freq=nz)
+    check_against_oracle(res, ref, group_sizes, 2.5e-5, ["noise_power_all", "noise_power_noautos"])
+    # the two sets' realisations are independent: the cross power of pure noise has no preferred phase
+    with pytest.raises(NotImplementedError):
+        RedundantPipeline(a["freq"], wins, a["pols"], a["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                          precision="complex128", nuv=2).process(
+            torch.as_tensor(vis, device=dev), torch.as_tensor(flags, device=dev), torch.as_tensor(ns, device=dev),
+            torch.as_tensor(a["int_time"], device=dev))
