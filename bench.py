@@ -546,6 +546,18 @@ def run_gpu_arm(args, cfg):
                  fused=bool(p128.fused), times_per_step=T)
         modes["hera350_complex128"] = m
         del p128
+        # two data sets (Nuv = 2): the batch cross-multiplied with a copy shifted by one baseline
+        T2 = max(T // 2, 1)
+        p2 = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
+                               precision="complex64", seed=0, nuv=2)
+        two = [torch.stack([x[:, :, :T2], torch.roll(x[:, :, :T2], 1, dims=1)]) for x in (vis, flags, nsample)]
+        m = time_pipeline(p2, (*two, int_time[:, :T2].contiguous()), T2, 5, peak)
+        m.update(config="hera350", precision="complex64", nuv=2, nfreq=p2.nfreq, nbls=p2.nbl, ngroups=p2.ngroup,
+                 fused=bool(p2.fused), times_per_step=T2,
+                 note="26 B per sample pair algorithmic; the data launch reads 18 B, the noise + thermal launch 10 B")
+        modes["hera350_nuv2_complex64"] = m
+        del p2, two
+        torch.cuda.empty_cache()
 
     line = None
     if rank == 0:

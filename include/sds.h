@@ -239,8 +239,9 @@ int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void
  * interleaved (re, im) doubles of twice the size:
  *   *_all  += (sum_i A2_i) conj(sum_j A1_j),    *_auto += sum_i A2_i conj(A1_i);
  * the in-kernel noise of set u is keyed by blk = (((s npol + p) 2 + u) ceil(nbl_total / 4) + (b >> 2))
- * ntime_total + t.  SDS_F32 plans with power-of-two windows of 64..1024 channels; thermal_coef must be
- * NULL (the thermal estimate of two sets: sds_thermal_power_avg with the two nsample arrays). */
+ * ntime_total + t.  SDS_F32 plans with power-of-two windows of 64..1024 channels.  The thermal estimate
+ * (delay_spectrum.py:3655-3707: N_ij = sqrt(n1_j n2_i), integration time of baseline j) rides in the
+ * noise launch: thermal_coef != NULL needs noise_mode 1 or 2. */
 
 /* ---- downstream estimators on the (averaged) spectra: SURVEY 8(f3) ----------------------
  * All arrays are C-ordered and viewed as (outer, n, inner) around the reduced / folded /

@@ -609,9 +609,11 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   SDS_CHECK_ARG(!thermal || (freq && pol_factor && int_time && thermal_all && thermal_auto),
                 "sds_engine_run: thermal needs freq, pol_factor, int_time and the thermal outputs");
   SDS_CHECK_ARG(d->nuv == 1 || d->nuv == 2, "sds_engine_run: nuv must be 1 or 2 (got %d)", d->nuv);
-  if (d->nuv == 2 && (pl.math != SDS_F32 || !pl.is_pow2 || N < 64 || N > 1024 || thermal || d->noise_mode == 3)) {
+  if (d->nuv == 2 && (pl.math != SDS_F32 || !pl.is_pow2 || N < 64 || N > 1024 || d->noise_mode == 3 ||
+                      (thermal && d->noise_mode == 0))) {
     set_error("sds_engine_run: two data sets (nuv = 2) take the fused path in complex64 with power-of-two "
-              "windows of 64..1024 channels, noise_mode 0..2 and no thermal leg (sds_thermal_power_avg)");
+              "windows of 64..1024 channels and noise_mode 1 or 2 (0 without the thermal leg, which rides "
+              "in the noise launch)");
     return SDS_ENOTSUP;
   }
   const bool pow2_path = pl.is_pow2 && N >= 64 && N <= 2048 && pl.team_tw_f;
@@ -688,7 +690,7 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
     if ((rc = run_engine_uv2(N, P, LEG_DATA, st, &g_last_launches)) != SDS_OK) return rc;
     if (legs & LEG_NOISE) {
       if ((rc = setup()) != SDS_OK) return rc;
-      rc = run_engine_uv2(N, P, LEG_NOISE, st, &g_last_launches);
+      rc = run_engine_uv2(N, P, LEG_NOISE | (legs & LEG_THERMAL), st, &g_last_launches);
     }
     return rc;
   }

@@ -11,7 +11,12 @@
 // two data sets' rows of one (baseline, time) -- or, in the noise launch, their two noise rows.
 // One launch per leg (LEG_DATA: 18 B per sample pair; LEG_NOISE: 10 B): the accumulators of all four
 // transforms do not fit the register budget of three CTAs per SM.  The thermal estimate of two data
-// sets goes through sds_thermal_power_avg (engine.py).
+// sets (delay_spectrum.py:3655-3707: N_ij = sqrt(n1_j n2_i), integration time of baseline j) rides in
+// the noise launch, which stages both nsample arrays anyway: with a_u = nsample_u^-1/2 every factor
+// separates,  sum_ij = sum_c w[c] (sum_i a2_i)(sum_j a1_j / t_j),  autos  sum_i a2_i a1_i / t_i,  and so
+// does the panel mask (masked_invalid, 3697): a trapezoid panel counts for a pair when both of its ends
+// are valid in set 1 for i and in set 0 for j (full sums + rare per-row deficits, as in the one-set
+// engine).
 #include "sds_engine.cuh"
 #include "sds_packed.cuh"
 
@@ -20,7 +25,7 @@ namespace sds {
 constexpr int UV_STAGES = 2;
 
 template <int N, int LEG> struct UvCfg {
-  static_assert(LEG == LEG_DATA || LEG == LEG_NOISE, "one leg per launch");
+  static_assert(LEG == LEG_DATA || LEG == LEG_NOISE || LEG == (LEG_NOISE | LEG_THERMAL), "one leg per launch");
   static constexpr bool DATA = LEG == LEG_DATA;
   static constexpr int TPR = N / 8;
   static constexpr int TEAM = TPR < 32 ? 32 : TPR;
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(UvCfg<N, LEG>::THREADS, UvCfg<N, LEG>::MINB)
 engine_uv2_kernel(const __grid_constant__ EngineParams P) {
   using C = UvCfg<N, LEG>;
   using FFT = TeamFftX<N>;
-  constexpr bool DATA = C::DATA;
+  constexpr bool DATA = C::DATA, THERMAL = (LEG & LEG_THERMAL) != 0;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t s0 = smem_u32(smem_raw);
@@ -167,6 +172,15 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
     f2 Sa[8], Sb[8], Cauto[8];  // per time: sums of the two sets' transforms; per item: sum_i A2_i conj(A1_i)
 #pragma unroll
     for (int r = 0; r < 8; ++r) Sa[r] = Sb[r] = Cauto[r] = 0ull;
+    // thermal sums per channel, packed over channel pairs (tau + TPR 2m, tau + TPR (2m + 1)):
+    // A = sum_i a2_i, B = sum_j a1_j / t_j, C = sum_i a2_i a1_i / t_i; dfc[]: what the panel mask removes
+    // (per panel q: [0..2] left-end, [3..5] right-end deficits of A, B, C), local memory, rare path
+    f2 tA[4], tB[4], tC[4];
+    float dfc[48];
+    bool dirty_time = false;
+    double th_all_acc = 0.0, th_auto_acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
 
     int ci0 = 0, ct = t0;
     int64_t it_off = (int64_t)b0 * P.ntime + t0;
@@ -208,6 +222,49 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
         const float *n0 = reinterpret_cast<const float *>(row) + tau;
         const float *n1 = reinterpret_cast<const float *>(row + C::VALB) + tau;
         const float rt = (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
+        // a_u = nsample_u^-1/2 (0 where invalid): shared by the noise amplitude and the thermal sums
+        float av0[8], av1[8];
+        bool all_ok = true;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float s0v = n0[TPR * r], s1v = n1[TPR * r];
+          const bool ok0 = active && s0v > 0.f, ok1 = active && s1v > 0.f;
+          av0[r] = ok0 ? fast_rsqrt(s0v) : 0.f;
+          av1[r] = ok1 ? fast_rsqrt(s1v) : 0.f;
+          all_ok = all_ok && ok0 && ok1;
+        }
+        if (THERMAL) {
+          const float itv = rt * rt;
+          const f2 it2 = f2_make(itv, itv);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const f2 a1 = f2_make(av1[2 * m], av1[2 * m + 1]);                 // set 1: baseline i
+            const f2 b0 = f2_mul(f2_make(av0[2 * m], av0[2 * m + 1]), it2);    // set 0: baseline j, 1 / t_j
+            tA[m] = f2_add(tA[m], a1);
+            tB[m] = f2_add(tB[m], b0);
+            tC[m] = f2_fma(a1, b0, tC[m]);
+          }
+          if (team_any<TEAM>(active && !all_ok, bar_id)) {
+            if (!dirty_time) {
+#pragma unroll 1
+              for (int k = 0; k < 48; ++k) dfc[k] = 0.f;
+              dirty_time = true;
+            }
+            if (active) {
+#pragma unroll 1
+              for (int q = 0; q < 8; ++q) {
+                if (tau + TPR * q + 1 >= N) continue;
+                const float l0 = n0[TPR * q], r0 = n0[TPR * q + 1], l1 = n1[TPR * q], r1 = n1[TPR * q + 1];
+                const bool vl0 = l0 > 0.f, vr0 = r0 > 0.f, vl1 = l1 > 0.f, vr1 = r1 > 0.f;
+                float *d = dfc + 6 * q;
+                if (vl1 != vr1) d[vl1 ? 0 : 3] += fast_rsqrt(vl1 ? l1 : r1);
+                if (vl0 != vr0) d[vl0 ? 1 : 4] += fast_rsqrt(vl0 ? l0 : r0) * itv;
+                const bool wl = vl0 && vl1, wr = vr0 && vr1;
+                if (wl != wr) d[wl ? 2 : 5] += wl ? fast_rsqrt(l0) * fast_rsqrt(l1) * itv : fast_rsqrt(r0) * fast_rsqrt(r1) * itv;
+              }
+            }
+          }
+        }
         if (P.noise_mode == 1) {
           const uint32_t bsel = (uint32_t)(blg + ia) & 3u;
           if (ci0 == 0 || bsel < (uint32_t)ROWS) {
@@ -218,11 +275,10 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
           const uint32_t w0 = engine_pick_mm(nw0, bsel), w1 = engine_pick_mm(nw1, bsel);
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const float s0v = n0[TPR * r], s1v = n1[TPR * r];
-            const bool k0 = active && fl0[TPR * r] == 0 && s0v > 0.f && ((w0 >> r) & 1u);
-            const bool k1 = active && fl1[TPR * r] == 0 && s1v > 0.f && ((w1 >> r) & 1u);
-            const float a0 = k0 ? (sigc[r] * rt) * fast_rsqrt(s0v) : 0.f;
-            const float a1 = k1 ? (sigc[r] * rt) * fast_rsqrt(s1v) : 0.f;
+            const bool k0 = fl0[TPR * r] == 0 && ((w0 >> r) & 1u);
+            const bool k1 = fl1[TPR * r] == 0 && ((w1 >> r) & 1u);
+            const float a0 = ((k0 ? sigc[r] : 0.f) * rt) * av0[r];
+            const float a1 = ((k1 ? sigc[r] : 0.f) * rt) * av1[r];
             va[r] = engine_signs_mm(a0, w0, r);
             vb[r] = engine_signs_mm(a1, w1, r);
           }
@@ -265,6 +321,59 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
           if (sub == 0) pw_s[tau + TPR * r] = f2_cmac_conj(pw_s[tau + TPR * r], sb, sa);
           Sa[r] = Sb[r] = 0ull;
         }
+        if (THERMAL) {
+          const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N + tau;
+          const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N + tau;
+          // the right end of a panel is the next channel: another thread's sums, through this row's
+          // exchange buffers ((A, B) pairs in the first, C in the second)
+          team_sync<TEAM>(bar_id);
+          float Ar[8], Br[8], Cr[8], Ap[8], Bp[8], Cp[8];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            Ar[2 * m] = f2_lo(tA[m]); Ar[2 * m + 1] = f2_hi(tA[m]);
+            Br[2 * m] = f2_lo(tB[m]); Br[2 * m + 1] = f2_hi(tB[m]);
+            Cr[2 * m] = f2_lo(tC[m]); Cr[2 * m + 1] = f2_hi(tC[m]);
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            sts_f2(xa + 8u * (uint32_t)(tau + TPR * r), f2_make(Ar[r], Br[r]));
+            sts_f32(xa + C::BUF + 4u * (uint32_t)(tau + TPR * r), Cr[r]);
+          }
+          team_sync<TEAM>(bar_id);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < 7 || tau + 1 < TPR) {  // no panel right of channel N - 1
+              const f2 nx = lds_f2(xa + 8u * (uint32_t)(tau + TPR * r + 1));
+              Ap[r] = f2_lo(nx); Bp[r] = f2_hi(nx);
+              Cp[r] = lds_f32(xa + C::BUF + 4u * (uint32_t)(tau + TPR * r + 1));
+            } else {
+              Ap[r] = Bp[r] = Cp[r] = 0.f;
+            }
+          }
+          if (dirty_time) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              Ar[r] -= dfc[6 * r + 0]; Br[r] -= dfc[6 * r + 1]; Cr[r] -= dfc[6 * r + 2];
+              Ap[r] -= dfc[6 * r + 3]; Bp[r] -= dfc[6 * r + 4]; Cp[r] -= dfc[6 * r + 5];
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            f2 ab = f2_make(Ar[r], Ap[r]), bb = f2_make(Br[r], Bp[r]);
+#pragma unroll
+            for (int off = TPR; off < 32; off <<= 1) {
+              ab = f2_add(ab, f2_shfl_xor(ab, off));
+              bb = f2_add(bb, f2_shfl_xor(bb, off));
+            }
+            const double l = __ldg(wlp + TPR * r), rr = __ldg(wrp + TPR * r);
+            if (sub == 0)
+              th_all_acc += l * (double)(f2_lo(ab) * f2_lo(bb)) + rr * (double)(f2_hi(ab) * f2_hi(bb));
+            th_auto_acc += l * (double)Cr[r] + rr * (double)Cp[r];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
+          dirty_time = false;
+        }
       }
     }
 
@@ -282,6 +391,19 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
         atomicAdd(out_auto + 2 * (obase + kshift), (double)f2_lo(ca));
         atomicAdd(out_auto + 2 * (obase + kshift) + 1, (double)f2_hi(ca));
         pw_s[tau + TPR * r] = 0ull;
+      }
+    }
+    if (THERMAL) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        th_all_acc += __shfl_xor_sync(0xffffffffu, th_all_acc, off);
+        th_auto_acc += __shfl_xor_sync(0xffffffffu, th_auto_acc, off);
+      }
+      if ((tl & 31) == 0) {
+        const double f = 1e-6 * __ldg(P.pol_factor + p);
+        const int64_t o = ((int64_t)gout * P.nspw + s) * P.npol + p;
+        atomicAdd(P.th_all + o, f * th_all_acc);
+        atomicAdd(P.th_auto + o, f * th_auto_acc);
       }
     }
   }
@@ -314,7 +436,9 @@ static int launch_uv2(const EngineParams &P, cudaStream_t st, int *launches) {
 
 template <int N>
 static int run_uv2_n(const EngineParams &P, int leg, cudaStream_t st, int *launches) {
-  return leg == LEG_DATA ? launch_uv2<N, LEG_DATA>(P, st, launches) : launch_uv2<N, LEG_NOISE>(P, st, launches);
+  if (leg == LEG_DATA) return launch_uv2<N, LEG_DATA>(P, st, launches);
+  if (leg == LEG_NOISE) return launch_uv2<N, LEG_NOISE>(P, st, launches);
+  return launch_uv2<N, LEG_NOISE | LEG_THERMAL>(P, st, launches);
 }
 
 int run_engine_uv2(int N, const EngineParams &P, int leg, cudaStream_t st, int *launches) {

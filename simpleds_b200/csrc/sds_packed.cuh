@@ -338,4 +338,34 @@ template <int N> struct TeamFftX {
   }
 };
 
+// ---- small helpers shared by the fused engines ------------------------------------------------
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// team-wide OR of a predicate (one vote for a warp-sized team, a reducing named barrier otherwise)
+template <int TEAM_THREADS>
+__device__ __forceinline__ bool team_any(bool pred, int barrier_id) {
+  if constexpr (TEAM_THREADS <= 32) {
+    return __any_sync(0xffffffffu, pred);
+  } else {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "barrier.red.or.pred q, %2, %3, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "r"(barrier_id), "n"(TEAM_THREADS)
+        : "memory");
+    return r != 0;
+  }
+}
+
 }  // namespace sds

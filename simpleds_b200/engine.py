@@ -214,9 +214,11 @@ class RedundantPipeline:
         if sub is not None and len(sub["index"]) == 0:
             return
         if self.fused:
-            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, thermal and self.nuv == 1, time_offset,
-                                ntot, subset=sub)
-            if thermal and self.nuv == 2:
+            # two data sets: the thermal sums ride in the noise launch; without noise they go through
+            # the chained kernels
+            in_kernel = thermal and (self.nuv == 1 or mode != 0)
+            self._process_fused(vis, fl, nsample, int_time, mode, noise_in, in_kernel, time_offset, ntot, subset=sub)
+            if thermal and not in_kernel:
                 self._thermal_two_sets(nsample, int_time, sub)
         else:
             if sub is not None:
@@ -490,4 +492,4 @@ class RedundantPipeline:
 
     def algorithmic_bytes(self, ntimes):
         distinct = len(set(c for w in self.win_start for c in range(w, w + self.nfreq)))
-        return 13 * self.npol * self.nbl * int(ntimes) * distinct
+        return 13 * self.nuv * self.npol * self.nbl * int(ntimes) * distinct
