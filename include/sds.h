@@ -113,10 +113,13 @@ int sds_noise_transform(const sds_plan *plan, const double *coef, const double *
 /* Materialised cross power, utils.py:387-389 as called at ds.py:3620-3633:
  * out[s,p,i,j,t,d] = a2[s,p,i,t,d] * conj(a1[s,p,j,t,d]).  a1/a2 have element
  * strides (stride_s, stride_p) over their first two axes and are contiguous in
- * (B,T,D); dtype SDS_C64|SDS_C128 for inputs and output alike. */
+ * (B,T,D); dtype SDS_C64|SDS_C128 for inputs and output alike.
+ * scale_sp: NULL, or fp64 [S][P]: out is multiplied by scale_sp[s][p] as it is written (the
+ * cosmological unit conversion of delay_spectrum.py:1306-1311, which the reference applies in a
+ * second pass over the tensor). */
 int sds_cross_power_full(const void *a1, const void *a2, int dtype, int S, int P,
                          int B, int T, int D, int64_t stride_s, int64_t stride_p,
-                         void *out, sds_stream stream);
+                         const double *scale_sp, void *out, sds_stream stream);
 
 /* Materialised thermal estimate, ds.py:3637-3707 + utils.py:230-278.
  * n1 = nsample of the conj ("j") side, n2 = of the "i" side (same pointer when
@@ -125,12 +128,13 @@ int sds_cross_power_full(const void *a1, const void *a2, int dtype, int S, int P
  * freq   fp64 [S][F] in Hz (trapezoid abscissa), int_time fp64 [B][T] (j side),
  * pol_factor fp64 [P] = 1 / (npols_noise * sqrt(2)).
  * out fp64 [S][P][B][B][T] in K^2 sr^2 Hz^6; invalid samples are masked out of
- * the trapezoid (their panels contribute 0). */
+ * the trapezoid (their panels contribute 0).  scale_sp: NULL, or fp64 [S][P] multiplied in as the
+ * tensor is written (the thermal conversion of delay_spectrum.py:1339-1343). */
 int sds_thermal_power_full(const void *n1, const void *n2, int nsample_dtype,
                            int64_t stride_s, int64_t stride_p, const double *coef,
                            const double *freq, const double *int_time,
                            const double *pol_factor, int S, int P, int B, int T, int F,
-                           double *out, sds_stream stream);
+                           const double *scale_sp, double *out, sds_stream stream);
 
 /* Pair sums of the thermal estimate per (group, spw, pol, time), same inputs as
  * sds_thermal_power_full plus the group table of sds_cross_power_avg:

@@ -60,9 +60,9 @@ _SIGNATURES = {
     "sds_generate_noise": (_i32, [_vp, _i64, _vp, _vp, _u64, _u64, _vp, _i32, _vp]),
     "sds_noise_transform": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _dbl,
                                    _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "sds_cross_power_full": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp]),
+    "sds_cross_power_full": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "sds_thermal_power_full": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
-                                      _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+                                      _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sds_thermal_power_avg": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32,
                                      _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sds_cross_power_avg": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64,

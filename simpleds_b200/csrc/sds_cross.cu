@@ -12,14 +12,18 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cross_power_full_kernel(const cpx<T> *__restrict__ a1, const cpx<T> *__restrict__ a2, int P,
                         int B, int64_t TD, int64_t stride_s, int64_t stride_p,
-                        cpx<T> *__restrict__ out) {
+                        const double *__restrict__ scale_sp, cpx<T> *__restrict__ out) {
   const int sp = blockIdx.z, i = blockIdx.y;
+  // per-(window, pol) factor (the cosmological conversion, delay_spectrum.py:1306-1311): applied
+  // to the i side once per element, in fp64, so the tensor is written once and already converted
+  const double sc = scale_sp ? scale_sp[sp] : 1.0;
   const int64_t in_base = (int64_t)(sp / P) * stride_s + (int64_t)(sp % P) * stride_p;
   const cpx<T> *a1p = a1 + in_base, *a2p = a2 + in_base + (int64_t)i * TD;
   cpx<T> *op = out + ((int64_t)sp * B + i) * B * TD;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < TD;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const cpx<T> x = a2p[e];
+    cpx<T> x = a2p[e];
+    if (scale_sp) x = {(T)((double)x.x * sc), (T)((double)x.y * sc)};
 #pragma unroll 4
     for (int j = 0; j < B; ++j) op[(int64_t)j * TD + e] = cmul_conj(x, a1p[(int64_t)j * TD + e]);
   }
@@ -123,12 +127,12 @@ cross_power_avg_pairs_kernel(const cpx<T> *__restrict__ a1, const cpx<T> *__rest
 
 template <typename T>
 static int run_full(const void *a1, const void *a2, int S, int P, int B, int64_t TD,
-                    int64_t stride_s, int64_t stride_p, void *out, cudaStream_t st) {
+                    int64_t stride_s, int64_t stride_p, const double *scale_sp, void *out, cudaStream_t st) {
   int64_t gx = (TD + 255) / 256;
   if (gx > 4096) gx = 4096;
   dim3 grid((unsigned)gx, B, S * P);
   cross_power_full_kernel<T><<<grid, 256, 0, st>>>((const cpx<T> *)a1, (const cpx<T> *)a2, P, B,
-                                                   TD, stride_s, stride_p, (cpx<T> *)out);
+                                                   TD, stride_s, stride_p, scale_sp, (cpx<T> *)out);
   SDS_LAUNCH_CHECK("cross_power_full_kernel");
   return SDS_OK;
 }
@@ -160,8 +164,8 @@ static int run_avg(const void *a1, const void *a2, int S, int P, int64_t TD, int
 }  // namespace sds
 
 extern "C" int sds_cross_power_full(const void *a1, const void *a2, int dtype, int S, int P, int B,
-                                    int T, int D, int64_t stride_s, int64_t stride_p, void *out,
-                                    sds_stream stream) {
+                                    int T, int D, int64_t stride_s, int64_t stride_p,
+                                    const double *scale_sp, void *out, sds_stream stream) {
   SDS_CHECK_ARG(a1 && a2 && out, "sds_cross_power_full: NULL pointer");
   SDS_CHECK_ARG(dtype == SDS_C64 || dtype == SDS_C128,
                 "sds_cross_power_full: dtype must be SDS_C64 or SDS_C128");
@@ -170,8 +174,8 @@ extern "C" int sds_cross_power_full(const void *a1, const void *a2, int dtype, i
   if ((int64_t)S * P * B * T * D == 0) return SDS_OK;
   const int64_t TD = (int64_t)T * D;
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == SDS_C64 ? sds::run_full<float>(a1, a2, S, P, B, TD, stride_s, stride_p, out, st)
-                          : sds::run_full<double>(a1, a2, S, P, B, TD, stride_s, stride_p, out, st);
+  return dtype == SDS_C64 ? sds::run_full<float>(a1, a2, S, P, B, TD, stride_s, stride_p, scale_sp, out, st)
+                          : sds::run_full<double>(a1, a2, S, P, B, TD, stride_s, stride_p, scale_sp, out, st);
 }
 
 extern "C" int sds_cross_power_avg(const void *a1, const void *a2, int dtype, int S, int P, int B,

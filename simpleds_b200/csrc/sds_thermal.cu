@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(TH_TILE *TH_TILE)
 thermal_full_kernel(const void *n1, const void *n2, int ns_dtype, int64_t stride_s,
                     int64_t stride_p, const double *__restrict__ coef,
                     const double *__restrict__ freq, const double *__restrict__ int_time,
-                    const double *__restrict__ pol_factor, int P, int B, int T, int F,
-                    double *__restrict__ out) {
+                    const double *__restrict__ pol_factor, const double *__restrict__ scale_sp, int P,
+                    int B, int T, int F, double *__restrict__ out) {
   __shared__ double Ll[TH_TILE][TH_KC + 1], Lr[TH_TILE][TH_KC + 1];
   __shared__ double Rl[TH_TILE][TH_KC + 1], Rr[TH_TILE][TH_KC + 1];
   const int ntile = (B + TH_TILE - 1) / TH_TILE;
@@ -73,7 +73,8 @@ thermal_full_kernel(const void *n1, const void *n2, int ns_dtype, int64_t stride
   if (i < B && j < B) {
     const double tj = int_time[(int64_t)j * T + t];
     const double v = (tj > 0.0) ? 1e-6 * pol_factor[p] * acc / tj : 0.0;
-    out[(((int64_t)sp * B + i) * B + j) * T + t] = v;
+    // optional per-(window, pol) factor: the thermal conversion of delay_spectrum.py:1339-1343
+    out[(((int64_t)sp * B + i) * B + j) * T + t] = scale_sp ? v * scale_sp[sp] : v;
   }
 }
 
@@ -154,7 +155,7 @@ extern "C" int sds_thermal_power_full(const void *n1, const void *n2, int nsampl
                                       int64_t stride_s, int64_t stride_p, const double *coef,
                                       const double *freq, const double *int_time,
                                       const double *pol_factor, int S, int P, int B, int T, int F,
-                                      double *out, sds_stream stream) {
+                                      const double *scale_sp, double *out, sds_stream stream) {
   SDS_CHECK_ARG(n1 && n2 && coef && freq && int_time && pol_factor && out,
                 "sds_thermal_power_full: NULL pointer");
   SDS_CHECK_ARG(nsample_dtype == SDS_F32 || nsample_dtype == SDS_F64,
@@ -167,7 +168,7 @@ extern "C" int sds_thermal_power_full(const void *n1, const void *n2, int nsampl
   const int ntile = (B + sds::TH_TILE - 1) / sds::TH_TILE;
   dim3 grid(ntile * ntile, T, S * P);
   sds::thermal_full_kernel<<<grid, sds::TH_TILE * sds::TH_TILE, 0, (cudaStream_t)stream>>>(
-      n1, n2, nsample_dtype, stride_s, stride_p, coef, freq, int_time, pol_factor, P, B, T, F, out);
+      n1, n2, nsample_dtype, stride_s, stride_p, coef, freq, int_time, pol_factor, scale_sp, P, B, T, F, out);
   SDS_LAUNCH_CHECK("thermal_full_kernel");
   return SDS_OK;
 }

@@ -595,12 +595,18 @@ class DelaySpectrum:
         if self.data_type == "frequency":
             self.delay_transform()
         j = 0 if self.Nuv == 1 else 1
-        unit = self._data_unit ** 2
-        self.power_array = Quantity(ops.cross_power_full(self._data[:, 0], self._data[:, j]), unit)
-        self.noise_power = Quantity(ops.cross_power_full(self._noise[:, 0], self._noise[:, j]), unit)
-        self.unit_conversion = self.thermal_conversion = None  # fresh arrays carry no conversion
-        self.calculate_thermal_sensitivity()
-        self.update_cosmology(cosmology=cosmology, littleh_units=littleh_units)
+        # The reference cross-multiplies, estimates the thermal power and then calls update_cosmology,
+        # which multiplies the three O(Nbls^2) tensors by a per-(window, pol) factor in a second pass
+        # (ds.py:3620-3635, 1306-1311, 1339-1343).  Here the factors are worked out first and ride in
+        # the kernels that write the tensors: every tensor is written once, already converted.
+        self.power_array = self.noise_power = self.thermal_power = None
+        self.unit_conversion = self.thermal_conversion = None
+        cv = self._cosmology_factors(cosmology, littleh_units, self._data_unit ** 2, want_thermal=True)
+        self.power_array = Quantity(ops.cross_power_full(self._data[:, 0], self._data[:, j],
+                                                         scale_sp=cv["power_scale"]), cv["power_unit"])
+        self.noise_power = Quantity(ops.cross_power_full(self._noise[:, 0], self._noise[:, j],
+                                                         scale_sp=cv["power_scale"]), cv["power_unit"])
+        self.calculate_thermal_sensitivity(scale_sp=cv["thermal_scale"], unit=cv["thermal_unit"])
 
     # ------------------------------------------------------------------ cosmology
     _LITTLEH_POWER = Unit("mK^2 Mpc^3 littleh^-3")
@@ -656,12 +662,13 @@ class DelaySpectrum:
         ops.check(rc, "sds_conversion_integral")
         return out.cpu().numpy()
 
-    def update_cosmology(self, cosmology=None, littleh_units=False):
-        """ds.py:1201-1365: redshift, k_parallel, k_perpendicular and the conversion of the power
-        estimates to mK^2 Mpc^3 (per (window, pol) integrals of nu^4 / X2Y * taper^2 * beam^2)."""
+    def _cosmology_factors(self, cosmology, littleh_units, power_unit, want_thermal):
+        """The state part of ds.py:1201-1365 -- cosmology, redshift, k_parallel, k_perpendicular,
+        unit_conversion, thermal_conversion -- and the per-(window, pol) factors that take power
+        estimates in ``power_unit`` (None: no power array) and the thermal estimate to mK^2 Mpc^3
+        (littleh folded in).  Returns dict(power_scale, power_unit, thermal_scale, thermal_unit)."""
         from . import cosmo as simple_cosmo
 
-        self.remove_cosmology()
         if cosmology is not None:
             if not isinstance(cosmology, simple_cosmo.FlatLambdaCDM):
                 raise ValueError("Input cosmology must a sub-class of astropy.cosmology.core.Cosmology")
@@ -673,45 +680,60 @@ class DelaySpectrum:
         delay_s = np.asarray(self.delay_array.value, dtype=np.float64) * 1e-9
         self.k_parallel = simple_cosmo.eta2kparr(Quantity(delay_s.reshape(1, self.Ndelays), "s"),
                                                  self.redshift.reshape(self.Nspws, 1), cosmo=self.cosmology)
+        self.k_perpendicular = None
         if self.uvw is not None:
             uvw_wave = np.linalg.norm(np.asarray(_value(self.uvw), dtype=np.float64)) / (
                 simple_cosmo.C_M_S / freq.mean(axis=1))
             self.k_perpendicular = simple_cosmo.u2kperp(uvw_wave, self.redshift, cosmo=self.cosmology)
+        out = dict(power_scale=None, power_unit=None, thermal_scale=None, thermal_unit=None)
         x2y = i4 = None
-        if self.power_array is not None or self.thermal_power is not None:
+        if power_unit is not None or want_thermal:
             x2y = simple_cosmo.X2Y(simple_cosmo.calc_z(self.freq_array), cosmo=self.cosmology).value
             with np.errstate(divide="ignore", invalid="ignore"):
                 i4 = self._conversion_integral(x2y, 4)
-        if self.power_array is not None:
+        h3 = (self.cosmology.H0 / 100.0) ** 3 if littleh_units else 1.0
+        if power_unit is not None:
             with np.errstate(divide="ignore", invalid="ignore"):
-                if self.power_array.unit == Unit("Jy^2 Hz^2"):
+                if power_unit == Unit("Jy^2 Hz^2"):
                     # (c^2 sr / 2 k_B)^2 / integral, SI -> mK^2 Mpc^3 / (Jy^2 Hz^2): K^2 -> mK^2, J -> 1e26 Jy m^2
                     conv = (simple_cosmo.C_M_S**2 / (2 * simple_cosmo.K_B)) ** 2 / i4 * 1e6 * 1e-52
                     self.unit_conversion = Quantity(conv, "mK^2 Mpc^3 Jy^-2 Hz^-2")
-                elif self.power_array.unit == Unit("K^2 sr^2 Hz^2"):
+                elif power_unit == Unit("K^2 sr^2 Hz^2"):
                     conv = 1.0 / self._conversion_integral(x2y, 0) * 1e6
                     self.unit_conversion = Quantity(conv, "mK^2 Mpc^3 K^-2 sr^-2 Hz^-2")
                 else:
                     self.unit_conversion = Quantity(np.ones((self.Nspws, self.Npols)), "")
-            unit = self.power_array.unit * self.unit_conversion.unit
+            unit = Unit(power_unit) * self.unit_conversion.unit
             if not self._data_unit == Unit("Hz"):
                 unit = Unit("mK^2 Mpc^3")
-            self.power_array = self._scale_sp(self.power_array, self.unit_conversion.value, unit)
-            self.noise_power = self._scale_sp(self.noise_power, self.unit_conversion.value, unit)
-        if self.thermal_power is not None:
+            out["power_scale"] = np.asarray(self.unit_conversion.value, dtype=np.float64) * h3
+            out["power_unit"] = self._LITTLEH_POWER if littleh_units else unit
+        if want_thermal:
             with np.errstate(divide="ignore", invalid="ignore"):
                 self.thermal_conversion = Quantity(1.0 / i4 * 1e6, "mK^2 Mpc^3 K^-2 sr^-2 Hz^-6")
-            self.thermal_power = self._scale_sp(self.thermal_power, self.thermal_conversion.value, "mK^2 Mpc^3")
+            out["thermal_scale"] = np.asarray(self.thermal_conversion.value, dtype=np.float64) * h3
+            out["thermal_unit"] = self._LITTLEH_POWER if littleh_units else Unit("mK^2 Mpc^3")
         if littleh_units:
             h = self.cosmology.H0 / 100.0
             self.k_parallel = Quantity(self.k_parallel.value / h, "littleh Mpc^-1")
             if self.k_perpendicular is not None:
                 self.k_perpendicular = Quantity(self.k_perpendicular.value / h, "littleh Mpc^-1")
-            if self.power_array is not None:
-                self.power_array = Quantity(self.power_array.value * h**3, self._LITTLEH_POWER)
-                self.noise_power = Quantity(self.noise_power.value * h**3, self._LITTLEH_POWER)
-            if self.thermal_power is not None:
-                self.thermal_power = Quantity(self.thermal_power.value * h**3, self._LITTLEH_POWER)
+        return out
+
+    def update_cosmology(self, cosmology=None, littleh_units=False):
+        """ds.py:1201-1365: redshift, k_parallel, k_perpendicular and the conversion of the power
+        estimates to mK^2 Mpc^3 (per (window, pol) integrals of nu^4 / X2Y * taper^2 * beam^2).
+        (``calculate_delay_spectrum`` applies the same factors inside the kernels that write the
+        tensors; this method re-scales tensors that already exist.)"""
+        self.remove_cosmology()
+        cv = self._cosmology_factors(cosmology, littleh_units,
+                                     None if self.power_array is None else self.power_array.unit,
+                                     want_thermal=self.thermal_power is not None)
+        if self.power_array is not None:
+            self.power_array = self._scale_sp(self.power_array, cv["power_scale"], cv["power_unit"])
+            self.noise_power = self._scale_sp(self.noise_power, cv["power_scale"], cv["power_unit"])
+        if self.thermal_power is not None:
+            self.thermal_power = self._scale_sp(self.thermal_power, cv["thermal_scale"], cv["thermal_unit"])
 
     def _thermal_inputs(self):
         freq = self.freq_array.value
@@ -722,13 +744,14 @@ class DelaySpectrum:
         npol = np.array([2 if p in np.arange(1, 5) else 1 for p in self.polarization_array])
         return coef, freq, 1.0 / (npol * np.sqrt(2))
 
-    def calculate_thermal_sensitivity(self):
-        """ds.py:3637-3707 -> thermal_power (Nspws,Npols,Nbls,Nbls,Ntimes), K^2 sr^2 Hz^6."""
+    def calculate_thermal_sensitivity(self, scale_sp=None, unit="K^2 sr^2 Hz^6"):
+        """ds.py:3637-3707 -> thermal_power (Nspws,Npols,Nbls,Nbls,Ntimes), K^2 sr^2 Hz^6 (times
+        ``scale_sp[s, p]`` and labelled ``unit`` when calculate_delay_spectrum passes the conversion)."""
         coef, freq, pf = self._thermal_inputs()
         j = 0 if self.Nuv == 1 else 1
         th = ops.thermal_power_full(self._nsample[:, 0], self._nsample[:, j], coef, freq,
-                                    self.integration_time.value, pf)
-        self.thermal_power = Quantity(th, "K^2 sr^2 Hz^6")
+                                    self.integration_time.value, pf, scale_sp=scale_sp)
+        self.thermal_power = Quantity(th, unit)
 
     def calculate_averaged_delay_spectrum(self, remove_autos=False, average_time=True,
                                           method="factorised"):

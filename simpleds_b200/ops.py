@@ -171,8 +171,18 @@ def _sp_strides(a):
     return a, int(st[0]), int(st[1])
 
 
-def cross_power_full(a1, a2=None):
-    """utils.py:387-389 with axis=2 on (S,P,B,T,D): out[s,p,i,j,t,d] = a2[i] conj(a1[j])."""
+def _scale_sp(scale_sp, S, P, dev):
+    if scale_sp is None:
+        return None
+    t = torch.as_tensor(np.asarray(scale_sp, dtype=np.float64), device=dev).contiguous()
+    if tuple(t.shape) != (S, P):
+        raise ValueError(f"scale_sp must have shape ({S}, {P})")
+    return t
+
+
+def cross_power_full(a1, a2=None, scale_sp=None):
+    """utils.py:387-389 with axis=2 on (S,P,B,T,D): out[s,p,i,j,t,d] = a2[i] conj(a1[j]), times
+    scale_sp[s,p] when given (the cosmological conversion, applied as the tensor is written)."""
     _lib.require_cuda()
     if a2 is None:
         a2 = a1
@@ -190,9 +200,10 @@ def cross_power_full(a1, a2=None):
         ss1, sp1 = a1.stride()[0], a1.stride()[1]
     S, P, B, T, D = a1.shape
     out = torch.empty((S, P, B, B, T, D), dtype=a1.dtype, device=a1.device)
+    sc = _scale_sp(scale_sp, S, P, a1.device)
     check(
         _lib.load().sds_cross_power_full(ptr(a1), ptr(a2), complex_dtype_code(a1), S, P, B, T, D,
-                                         ss1, sp1, ptr(out), stream_ptr()),
+                                         ss1, sp1, ptr(sc), ptr(out), stream_ptr()),
         "sds_cross_power_full",
     )
     return out
@@ -233,9 +244,9 @@ def cross_power_sums(a1, a2=None, group_offset=None, method="factorised"):
     return out_all, out_auto
 
 
-def thermal_power_full(n1, n2, coef, freq, int_time, pol_factor):
+def thermal_power_full(n1, n2, coef, freq, int_time, pol_factor, scale_sp=None):
     """ds.py:3637-3707.  n1/n2 (S,P,B,T,F) real; coef (S,P,F); freq (S,F);
-    int_time (B,T); pol_factor (P,) -> (S,P,B,B,T) f64."""
+    int_time (B,T); pol_factor (P,) -> (S,P,B,B,T) f64, times scale_sp[s,p] when given."""
     _lib.require_cuda()
     if tuple(n1.shape) != tuple(n2.shape):
         raise ValueError(
@@ -259,10 +270,11 @@ def thermal_power_full(n1, n2, coef, freq, int_time, pol_factor):
             or tuple(pf.shape) != (P,):
         raise ValueError("thermal_power_full: inconsistent shapes")
     out = torch.empty((S, P, B, B, T), dtype=torch.float64, device=dev)
+    sc = _scale_sp(scale_sp, S, P, dev)
     check(
         _lib.load().sds_thermal_power_full(ptr(n1), ptr(n2), real_dtype_code(n1), ss1, sp1,
                                            ptr(coef), ptr(freq), ptr(it), ptr(pf), S, P, B, T, F,
-                                           ptr(out), stream_ptr()),
+                                           ptr(sc), ptr(out), stream_ptr()),
         "sds_thermal_power_full",
     )
     return out
