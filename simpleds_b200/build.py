@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsds.so")
 SOURCES = [
-    "sds_api.cu", "sds_fft_generic.cu", "sds_fft_pow2.cu", "sds_fft_bluestein.cu", "sds_elementwise.cu",
+    "sds_api.cu", "sds_fft_generic.cu", "sds_fft_pow2.cu", "sds_fft_tma.cu", "sds_fft_bluestein.cu", "sds_elementwise.cu",
     "sds_cross.cu", "sds_thermal.cu", "sds_engine.cu", "sds_engine_f32.cu", "sds_engine_blue.cu", "sds_engine_uv2.cu",
     "sds_estimators.cu", "sds_cosmo.cu", "sds_ingest.cu",
 ]

@@ -152,6 +152,13 @@ int launch_pow2(const Plan &pl, const void *in, int in_dtype, int64_t in_row_str
                 const int32_t *win_start, double delta_x, void *out, int out_dtype,
                 cudaStream_t st);
 
+// complex64 fast path with bulk-TMA staging (sds_fft_tma.cu); SDS_ENOTSUP when the layout is not
+// 16-byte aligned or the plan is not SDS_F32
+int launch_pow2_tma(const Plan &pl, const void *in, int in_dtype, int64_t in_row_stride,
+                    const uint8_t *flags, int64_t flag_row_stride, int64_t nrows, int nwin,
+                    const int32_t *win_start, double delta_x, void *out, int out_dtype,
+                    cudaStream_t st);
+
 // non-power-of-two lengths (sds_fft_bluestein.cu); SDS_ENOTSUP when the plan has no tables
 int launch_bluestein(const Plan &pl, const void *in, int in_dtype, int64_t in_row_stride,
                      const uint8_t *flags, int64_t flag_row_stride, int64_t nrows, int nwin,
@@ -184,8 +191,11 @@ extern "C" int sds_delay_transform(const sds_plan *plan, const void *in, int in_
   if (nrows == 0) return SDS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (!inverse && pl.is_pow2) {
-    int rc = sds::launch_pow2(pl, in, in_dtype, in_row_stride, flags, flag_row_stride, nrows,
-                              nwin, win_start, delta_x, out, out_dtype, st);
+    int rc = sds::launch_pow2_tma(pl, in, in_dtype, in_row_stride, flags, flag_row_stride, nrows,
+                                  nwin, win_start, delta_x, out, out_dtype, st);
+    if (rc != SDS_ENOTSUP) return rc;
+    rc = sds::launch_pow2(pl, in, in_dtype, in_row_stride, flags, flag_row_stride, nrows, nwin,
+                          win_start, delta_x, out, out_dtype, st);
     if (rc != SDS_ENOTSUP) return rc;
   }
   if (!inverse && pl.blue_m) {
