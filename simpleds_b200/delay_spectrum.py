@@ -17,7 +17,9 @@ import torch
 from scipy.signal import windows
 
 from . import ops, utils
+from .io import DelaySpectrumIO, read_uvh5
 from .units import Quantity, Unit, UnitConversionError, is_quantity
+from .utils import jy_to_mk
 
 
 def _value(x):
@@ -61,6 +63,12 @@ class UVDataLite:
         self.Nants_data = len(ants)
         self.Nants_telescope = int(Nants_telescope) if Nants_telescope else self.Nants_data
 
+    @classmethod
+    def from_uvh5(cls, path):
+        """Read a UVH5 visibility file (what the reference does through pyuvdata's ``UVData.read``)
+        with the package's own HDF5 reader; the result feeds ``DelaySpectrum.add_uvdata``."""
+        return read_uvh5(path, cls)
+
     def get_baseline_nums(self):
         return np.unique(self.baseline_array)
 
@@ -85,7 +93,7 @@ class UVDataLite:
         return groups, centers, [float(np.linalg.norm(c)) for c in centers], []
 
 
-class DelaySpectrum:
+class DelaySpectrum(DelaySpectrumIO):
     """See module docstring.  ``precision`` = "complex128" (fp64 math, the
     reference's dtype) or "complex64" (fp32 math)."""
 
@@ -392,6 +400,10 @@ class DelaySpectrum:
         this.Nants_data, this.Nants_telescope = uv.Nants_data, uv.Nants_telescope
         this.x_orientation = uv.x_orientation
         this.generate_noise()  # all zeros while beam/trcvr are inf  (ds.py:987)
+        if this._data_unit == Unit("K sr"):
+            # visibilities in K sr: the noise (drawn in Jy) is converted too (ds.py:989-994)
+            j2k = torch.as_tensor(np.asarray(jy_to_mk(this.freq_array.value).value), device=this._noise.device)
+            this._noise = this._noise * j2k.reshape(this.Nspws, 1, 1, 1, 1, this.Nfreqs).to(this._noise.real.dtype)
         if this._data_unit == Unit(""):
             warnings.warn(
                 "Data is uncalibrated. Unable to covert noise array "

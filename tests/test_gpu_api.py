@@ -1,6 +1,7 @@
 """GPU parity tests of the reference-facing API (utils mirror + DelaySpectrum)
 against the oracle and the golden vectors.  Everything here goes through the C
 ABI of libsds.so."""
+import os
 import warnings
 
 import numpy as np
@@ -449,3 +450,87 @@ def test_noise_transform_is_the_chain_of_the_three_calls(cuda_device, precision)
         want_f = ops.generate_noise(sig, seed=5, normals=normals, out_dtype=cdt)
         want_d = ops.delay_transform(plan, want_f.reshape(-1, F), fl.reshape(-1, F), 97656.25)
         assert torch.equal(nf, want_f) and torch.equal(nd.reshape(-1), want_d.reshape(-1))
+
+
+def test_delay_spectrum_file_round_trip_and_write_partial(cuda_device, tmp_path):
+    """delay_spectrum.py:2423-3194: write -> read gives the object back ((Jy Hz)^2 units: the
+    cosmological conversion is taken out for the file and restored afterwards); a file initialised
+    from the whole object and filled by write_partial from two time slices equals the whole write."""
+    from simpleds_b200 import DelaySpectrum, hdf5lite
+    from simpleds_b200.units import Unit
+
+    pr = make_group(seed=12, P=2, B=4, T=6, F=32)
+    lst = 0.1 + 1e-3 * np.arange(6)
+
+    def build(sl):
+        ds = DelaySpectrum.from_arrays(
+            pr["vis"][..., sl, :], pr["flags"][..., sl, :], pr["nsample"][..., sl, :], pr["freq_array_hz"],
+            pr["integration_time_s"][:, sl], pr["polarization_array"], trcvr=pr["trcvr_k"], beam_area=pr["beam_area_sr"],
+            precision="complex128", lst_array=lst[sl], baseline_array=np.array([67611, 69637, 71714, 73763]),
+            uvw=[30.0, 0.0, 0.0], noise_seed=3)
+        ds.select_spectral_windows([(0, 15), (16, 31)])
+        ds.calculate_delay_spectrum()
+        return ds
+
+    whole = build(slice(0, 6))
+    assert whole.power_array.unit == Unit("mK^2 Mpc^3")
+    path = str(tmp_path / "whole.h5")
+    with pytest.warns(UserWarning, match="cosmological units"):
+        whole.write(path)
+    assert whole.power_array.unit == Unit("mK^2 Mpc^3")  # restored (ds.py:2739-2741)
+    with pytest.raises(IOError):
+        whole.write(path)
+    f = hdf5lite.File(path)
+    assert f.keys("/") == ["Data", "Header"] and f.attrs("Data/data_power")["unit"] == "Hz^2 Jy^2"
+    assert f.shape("Data/data_power") == (2, 2, 4, 4, 6, 16) and f.read("Data/thermal_power").dtype == np.float64
+    back = DelaySpectrum(precision="complex128").read(path)
+    assert (back.Nspws, back.Nuv, back.Npols, back.Nbls, back.Ntimes, back.Nfreqs) == (2, 1, 2, 4, 6, 16)
+    assert back.data_type == "delay" and back.vis_units == "Jy" and back.data_array.unit == Unit("Jy Hz")
+    np.testing.assert_array_equal(back.data_array.numpy(), whole.data_array.numpy())
+    np.testing.assert_array_equal(back.flag_array.cpu().numpy(), whole.flag_array.cpu().numpy())
+    np.testing.assert_array_equal(back.freq_array.value, whole.freq_array.value)
+    np.testing.assert_array_equal(back.baseline_array, whole.baseline_array)
+    back.update_cosmology()  # the file's (Jy Hz)^2 power back to mK^2 Mpc^3
+    np.testing.assert_allclose(back.power_array.numpy(), whole.power_array.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(back.thermal_power.numpy(), whole.thermal_power.numpy(), rtol=1e-12)
+    # streamed sink: the file laid out once, filled by two time slices
+    part = str(tmp_path / "partial.h5")
+    whole.initialize_save_file(part)
+    assert not hdf5lite.File(part).read("Data/data_power").any()
+    with pytest.raises(AssertionError):
+        whole.write_partial(str(tmp_path / "missing.h5"))
+    with pytest.warns(UserWarning, match="cosmological units"):
+        build(slice(0, 2)).write_partial(part)
+        build(slice(2, 6)).write_partial(part)
+    a, b = hdf5lite.File(path), hdf5lite.File(part)
+    for name in ("visdata", "flags", "data_power", "thermal_power"):
+        np.testing.assert_array_equal(a.read("Data/" + name), b.read("Data/" + name), err_msg=name)
+    # the noise realisation of a time slice is its own draw: only its shape and unit are compared
+    assert b.read("Data/visnoise").shape == a.read("Data/visnoise").shape
+    np.testing.assert_allclose(a.read("Data/nsamples"), b.read("Data/nsamples"))
+
+
+def test_uvdatalite_from_uvh5_feeds_add_uvdata(cuda_device, tmp_path):
+    """The real-file front end: a UVH5 file (here written from the fixture cut out of the
+    reference's test_redundant_array_odd_file.uvh5, old 4-D axis order) is read with the package's
+    own HDF5 reader and goes through add_uvdata (baseline numbers of t_ds.py:271-289).
+    tests/test_hdf5lite.py reads the h5py-written original where it exists."""
+    from simpleds_b200 import DelaySpectrum, hdf5lite
+    from simpleds_b200.delay_spectrum import UVDataLite
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "uvh5_odd.npz"))
+    path = str(tmp_path / "odd.uvh5")
+    w = hdf5lite.Writer(path)
+    w.create_dataset("Data/visdata", g["data_array"][:, None])
+    w.create_dataset("Data/flags", g["flag_array"][:, None])
+    w.create_dataset("Data/nsamples", g["nsample_array"][:, None])
+    for k in ("ant_1_array", "ant_2_array", "lst_array", "integration_time", "uvw_array", "polarization_array"):
+        w.create_dataset("Header/" + k, g[k])
+    w.create_dataset("Header/freq_array", g["freq_array"][None])
+    w.create_dataset("Header/vis_units", str(g["vis_units"]).encode())
+    w.create_dataset("Header/Nants_telescope", np.int64(g["Nants_telescope"]))
+    w.close()
+    uv = UVDataLite.from_uvh5(path)
+    assert np.array_equal(uv.data_array, g["data_array"]) and uv.vis_units == "Jy" and uv.Nbls == 51
+    ds = DelaySpectrum(uv=uv)
+    assert ds.Nbls == 51 and ds.Ntimes == 21 and ds.Nfreqs == 21 and ds.baseline_array[0] == 67611
