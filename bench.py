@@ -34,13 +34,13 @@ UNIT = "pair-spectra/s"
 CONFIGS = {
     # name: (array, nchan, nwin, npol, f0, df, t_int)
     "hera350": dict(array="hera_350", nchan=1024, nwin=4, npol=4, f0=100e6, df=97656.25, t_int=10.7,
-                    pols=[-5, -6, -7, -8], seed=1003),
+                    pols=[-5, -6, -7, -8], seed=1003, ntimes=1000),
     # BASELINE.json configs[1]: 203 channels.  The fused path stages rows in 16-channel units, so the
     # row pitch is 208 channels and the ONE spectral window is channels 0..202 (nfreq = 203)
     "paper64": dict(array="paper_grid", nchan=208, nwin=1, npol=2, f0=100e6, df=492610.84375, t_int=42.95,
-                    pols=[1, 2], seed=1002, windows=[(0, 202)]),
+                    pols=[1, 2], seed=1002, windows=[(0, 202)], ntimes=100),
     "ska512": dict(array="ska_512", nchan=2048, nwin=1, npol=2, f0=50e6, df=146484.375, t_int=0.85,
-                   pols=[-5, -6], seed=1005),
+                   pols=[-5, -6], seed=1005, ntimes=64),
 }
 
 
@@ -161,7 +161,7 @@ def workload_config(args, cfg, pipe):
     c = dict(
         workload=f"{args.config}: synthetic {cfg['array']} redundant array, {cfg['nchan']} channels in "
                  f"{cfg['nwin']} spectral windows, {cfg['npol']} pols, Blackman-Harris taper, "
-                 f"{args.times} times per step per GPU (streamed batches of the 1000-time job), "
+                 f"{args.times} times per step per GPU (streamed batches of the {cfg['ntimes']}-time job), "
                  "delay transform + noise realisation + redundant pair average + thermal estimate",
         times_per_step_per_gpu=args.times, precision=args.precision,
         l2_policy="inputs larger than L2 (no flush needed)",
@@ -343,7 +343,7 @@ def run_gpu_arm(args, cfg):
     pipe = RedundantPipeline(freq, wins, cfg["pols"], red["group_offset"], trcvr_k=144.0, beam_area_sr=0.76,
                              precision=args.precision, seed=0)
     T = args.times
-    ntime_total = 1000
+    ntime_total = max(cfg["ntimes"], T)  # the configuration's whole job (BASELINE.json configs)
     # this rank's resident batch (generation is not timed)
     vis, flags, nsample, int_time = synth.make_visibilities(
         red["group_offset"], cfg["npol"], T, freq, seed=cfg["seed"], device=dev, t_int=cfg["t_int"],
@@ -424,7 +424,7 @@ def run_gpu_arm(args, cfg):
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=measured_traffic(args, T), peak_source=peak_src, bytes_per_launch=alg_bytes,
                     kernel_ms=kern_ms, kernel="sds::engine_f32_kernel (+ engine_setup_kernel)"
-                    if args.precision == "complex64" else "sds::engine_kernel<double> x3 (+ setup)")
+                    if args.precision == "complex64" else "sds::engine_kernel<double, N, data> + sds::engine_f32_kernel<N, noise | thermal64> (+ setup each)")
 
     # per-leg breakdown of the fused kernel (explains the roofline fraction): same batch,
     # noise and/or thermal legs switched off
@@ -450,7 +450,7 @@ def run_gpu_arm(args, cfg):
             step(i)
         torch.cuda.synchronize()
 
-    # the fixed 1000-time job (BASELINE.json configs[2] / [3]): its 1000 / T batches dealt to the
+    # the configuration's fixed job (HERA-350: 1000 times, BASELINE.json configs[2] / [3]): its batches of T times dealt to the
     # ranks, one reduce at the end; at N = 1 this is the sustained number of the whole job, over N
     # it is the STRONG scaling of the path (the headline `value` is weak scaling).  Clocks sampled.
     fixed_job = None
