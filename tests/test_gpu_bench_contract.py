@@ -37,6 +37,16 @@ def test_bench_line_has_the_contract_keys(cuda_device):
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert e["value"] < d["value"]  # host buffers + PCIe can only be slower than HBM-resident
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # round 2: every BASELINE.json configuration in the same line, the fixed job, the H2D ceiling
+    assert set(r["modes"]) >= {"hera350_complex128", "hera350_nuv2_complex64", "ska512_complex64", "ska512_complex128",
+                               "paper64_203ch_complex64"}
+    assert r["modes"]["paper64_203ch_complex64"]["nfreq"] == 203 and r["modes"]["ska512_complex64"]["nfreq"] == 2048
+    assert all(m["fused"] and 0.01 < m["frac"] < 1.2 for m in r["modes"].values())
+    assert set(r["legs"]) == {"transform+pair_sums", "transform+pair_sums+thermal", "transform+pair_sums+noise"}
+    fj = d["fixed_job"]
+    assert fj["times"] == 1000 and fj["scaling"] == "strong" and fj["value"] > 1e9 and "clocks" in fj
+    assert 0 < e["frac_of_h2d_ceiling"] < 1.3 and e["d2h_bytes_per_job"] >= e["d2h_bytes_per_step"]
+    assert d["multi_gpu_check"] is None  # one GPU
 
 
 def test_reference_arm_line():
