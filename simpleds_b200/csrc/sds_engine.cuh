@@ -250,6 +250,22 @@ __device__ __forceinline__ uint32_t engine_pick_mm(const u32x4 &w, uint32_t sel)
   const uint32_t a = (sel & 1u) ? w.y : w.x, b = (sel & 1u) ? w.w : w.z;
   return (sel & 2u) ? b : a;
 }
+// the two multipliers of a sample: dsel = unflagged ? a : 0 (data), nsel = unflagged and on-bit ? b : 0
+// (noise); one predicate chain (flag test, bit test AND-ed into it) instead of three selects
+__device__ __forceinline__ void engine_selects_mm(uint32_t flag, uint32_t word, uint32_t bit, float a, float b,
+                                                  float &dsel, float &nsel) {
+  asm("{\n"
+      ".reg .pred pk, pn;\n"
+      ".reg .b32 t;\n"
+      "setp.eq.u32 pk, %2, 0;\n"
+      "and.b32 t, %3, %4;\n"
+      "setp.ne.and.u32 pn, t, 0, pk;\n"
+      "selp.f32 %0, %5, 0f00000000, pk;\n"
+      "selp.f32 %1, %6, 0f00000000, pn;\n"
+      "}\n"
+      : "=f"(dsel), "=f"(nsel)
+      : "r"(flag), "r"(word), "r"(bit), "f"(a), "f"(b));
+}
 // (re, im) = (+-amp, +-amp) for sample r of the word
 __device__ __forceinline__ unsigned long long engine_signs_mm(float amp, uint32_t word, int r) {
   const uint32_t ab = __float_as_uint(amp);

@@ -20,6 +20,15 @@ namespace sds {
 #ifndef E3_MIN_THREADS
 #define E3_MIN_THREADS 128
 #endif
+#ifndef E3_IL
+#define E3_IL 1  // interleaved 128-bit exchange of the two lockstep transforms
+#endif
+#ifndef E3_KEEP
+#define E3_KEEP 1
+#endif
+#ifndef E3_TV
+#define E3_TV 1
+#endif
 #ifndef E3_WARPS_PER_SM
 #define E3_WARPS_PER_SM 12  // register budget: 65536 / (12 * 32) = 170 per thread
 #endif
@@ -42,12 +51,19 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   static constexpr int ROWB = VISB + 5 * N;             // vis 8N (data leg only) | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = N * 8;                     // one exchange buffer of one row
-  static constexpr int XREGION = NWORKER * ROWS * 2 * BUF;  // all exchange buffers, aligned to BUF
+  // data and noise transforms in lockstep exchange through ONE padded buffer of 16-byte (data, noise)
+  // slots with 128-bit accesses (TeamFftX::run2_il): 18 N bytes per row, no alignment requirement;
+  // otherwise a pair of XOR-addressed buffers of 8 N bytes, aligned to 8 N
+  static constexpr bool IL = E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE);
+  static constexpr int XROW = IL ? TeamFftX<N>::IL_BYTES : 2 * BUF;  // exchange bytes of one row
+  static constexpr int XALIGN = IL ? 128 : BUF;
+  static constexpr int XREGION = NWORKER * ROWS * XROW;  // all exchange buffers
   static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
-  // per worker: 64 B barriers | E3_STAGES slots | 2 N floats (P sums)
-  static constexpr int WORKER_BYTES = 64 + E3_STAGES * SLOT + 8 * N;
-  // BUF bytes of slack in front: the exchange region is aligned to BUF at run time
-  static constexpr int SMEM = BUF + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
+  // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
+  static constexpr int HEAD = 192;
+  static constexpr int WORKER_BYTES = HEAD + E3_STAGES * SLOT + 8 * N;
+  // XALIGN bytes of slack in front: the exchange region is aligned at run time
+  static constexpr int SMEM = XALIGN + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
 
 template <int N, int LEGS, bool GAUSS>
@@ -63,25 +79,39 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   using C = E3Cfg<N, LEGS, GAUSS>;
   using FFT = TeamFftX<N>;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
+  constexpr bool TV = E3_TV && ROWS == 1 && (HAS_N || HAS_T || T64);  // integration times as a lane vector
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // exchange region first, aligned to the size of one buffer (TeamFftX addressing)
   const uint32_t s0 = smem_u32(smem_raw);
-  unsigned char *smem = smem_raw + (((s0 + C::BUF - 1u) & ~(uint32_t)(C::BUF - 1)) - s0);
+  unsigned char *smem = smem_raw + (((s0 + C::XALIGN - 1u) & ~(uint32_t)(C::XALIGN - 1)) - s0);
 
-  f2 *tw_s = reinterpret_cast<f2 *>(smem + C::XREGION);
-  for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
-    tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   // 0 at run time (P.zero is 0), lane-dependent as far as ptxas can tell: see the int_time load
   const int lane_zero = (int)(threadIdx.x & 31u) * P.zero;
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;
+  // Shared-space addresses, each passed through an empty asm: ptxas otherwise re-derives them from
+  // the CTA's shared window (SR_CgaCtaId, the run-time alignment, the warp index) at every use inside
+  // the step loop -- some forty instructions per row
+  uint32_t sb_a = smem_u32(smem);
+#if E3_KEEP
+  asm volatile("" : "+r"(sb_a));
+#endif
+  f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
+  for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
+    tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
   // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
-  const uint32_t xa = smem_u32(smem) + (uint32_t)((wid * ROWS + sub) * 2) * C::BUF;
-  const typename FFT::Addr fa = FFT::make_addr(xa, tau);
-  unsigned char *wbase = smem + C::XREGION + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
+  uint32_t xa = sb_a + (uint32_t)(wid * ROWS + sub) * C::XROW;
+  uint32_t wb_a = sb_a + C::XREGION + C::TW_BYTES + (uint32_t)wid * C::WORKER_BYTES;
+#if E3_KEEP
+  asm volatile("" : "+r"(xa));
+  asm volatile("" : "+r"(wb_a));
+#endif
+  const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : FFT::make_addr(xa, tau);
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(__cvta_shared_to_generic(wb_a));
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
-  unsigned char *stages = wbase + 64;
-  const uint32_t full_a = smem_u32(full), stages_a = smem_u32(stages);  // shared-space addresses
+  unsigned char *stages = wbase + C::HEAD;
+  const uint32_t tv_a = wb_a + 64;  // [32] floats: integration times of the next steps
+  const uint32_t full_a = wb_a, stages_a = wb_a + C::HEAD;  // shared-space addresses
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
   float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT);
   for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
@@ -205,6 +235,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
+    const int64_t it0 = it_off;
     // Philox counter words 0, 1 of (row 0, time t0):
     // row_id = ((s npol + p) nbl_total + b) ntime_total + t   (include/sds.h)
     uint64_t rid_t = (((uint64_t)((int64_t)s * P.npol + p) * (uint64_t)P.nbl_total +
@@ -219,16 +250,44 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
     // on the critical path of every row)
     float tint_next = 1.f;
-    if (HAS_N || HAS_T || T64)
+    if (!TV && (HAS_N || HAS_T || T64))
       tint_next = __ldg(P.int_time + it_off + (int64_t)((ROWS == 1 || sub < ng) ? sub : 0) * P.ntime);
+    // one row per step: entry (f & 31) of a small shared-memory ring holds the integration time of
+    // step f of the item (t_int^-1/2 unless the fp64 thermal sums need the value itself); the half of
+    // the ring that is not being consumed is refilled every 16 steps, 16 to 31 steps ahead of its use,
+    // and a row takes its value with one broadcast load instead of an address computation and an L2 load
+    auto tv_fill = [&](int f) {
+      float v = 0.f;
+      if (f < nsteps) {
+        // f / ng without a hoisted reciprocal (registers): approximate quotient, exact fix-up
+        float rcp;
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)ng));
+        int tt = (int)((float)f * rcp), ii = f - tt * ng;
+        if (ii < 0) { ii += ng; --tt; }
+        if (ii >= ng) { ii -= ng; ++tt; }
+        v = __ldg(P.int_time + it0 + (int64_t)ii * P.ntime + tt);
+        if (!T64) v = v > 0.f ? fast_rsqrt(v) : 0.f;
+      }
+      sts_f32(tv_a + 4u * (uint32_t)(f & 31), v);
+    };
+    if (TV) {
+      team_sync<TEAM>(bar_id);  // the previous item's last reads of the ring are done
+      if ((threadIdx.x & 16u) == 0) tv_fill((int)(threadIdx.x & 15u));
+    }
     for (int step = 0; step < nsteps; ++step) {
       team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
       if (pleft > 0) issue();
       const int i = ci0 + sub;
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
-      const float tint = tint_next;
-      if ((HAS_N || HAS_T || T64) && step + 1 < nsteps) {
+      float tint = tint_next;
+      if constexpr (TV) {
+        // (every warp of a team writes the same values; the step's team sync orders them before the reads)
+        if ((step & 15) == 0 && (((int)threadIdx.x ^ step) & 16) != 0)
+          tv_fill(step + 16 + (int)(threadIdx.x & 15u));
+        tint = lds_f32(tv_a + 4u * (uint32_t)(step & 31));
+      }
+      if (!TV && (HAS_N || HAS_T || T64) && step + 1 < nsteps) {
         const bool wrap = ci0 + ROWS >= ng;
         const int ni = (wrap ? 0 : ci0 + ROWS) + sub;
         // lane_zero (= 0 at run time, but lane-dependent as far as ptxas can tell) keeps the address, and with it
@@ -245,7 +304,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       const unsigned char *fl_s = row + C::VISB + 4 * N + tau;
 
       // rt = t_int^-1/2, itv = 1 / t_int (0 where the integration time is not positive)
-      const float rt = (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
+      const float rt = (TV && !T64) ? tint : (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
       const float itv = rt * rt;
       // a = nsample^-1/2 (0 where invalid): shared by the noise amplitude and the thermal sums
       float av[8];
@@ -276,11 +335,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         const uint32_t word = engine_pick_mm(nwords, bsel);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const bool k = active && fl_s[TPR * r] == 0;
-          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, k ? tapdf[r] : 0.f);
           // sigma = coef / sqrt(t_int nsample) (ds.py:3546-3581); the on/off bit rides on the flag select
-          const bool kn = k && ((word >> r) & 1u);
-          const float amp = ((kn ? sigc[r] : 0.f) * rt) * av[r];
+          float dsel, nsel;
+          engine_selects_mm(active ? (uint32_t)fl_s[TPR * r] : 1u, word, 1u << r, tapdf[r], sigc[r], dsel, nsel);
+          if (HAS_D) vd[r] = f2_scale(active ? vis_s[TPR * r] : 0ull, dsel);
+          const float amp = (nsel * rt) * av[r];
           vn[r] = engine_signs_mm(amp, word, r);
         }
       } else if (HAS_N && GAUSS && P.noise_mode == 1) {
@@ -308,9 +367,21 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
         }
       }
+      if (HAS_T) {  // thermal sums first: nsample^-1/2 is dead before the transforms start
+        const f2 it2 = f2_make(itv, itv);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const f2 aa = f2_make(av[2 * m], av[2 * m + 1]);
+          const f2 ab = f2_mul(aa, it2);
+          tA[m] = f2_add(tA[m], aa);
+          tB[m] = f2_add(tB[m], ab);
+          tC[m] = f2_fma(aa, ab, tC[m]);
+        }
+      }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
+        if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
+        else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -329,15 +400,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
 
       if (HAS_T) {
-        const f2 it2 = f2_make(itv, itv);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const f2 aa = f2_make(av[2 * m], av[2 * m + 1]);
-          const f2 ab = f2_mul(aa, it2);
-          tA[m] = f2_add(tA[m], aa);
-          tB[m] = f2_add(tB[m], ab);
-          tC[m] = f2_fma(aa, ab, tC[m]);
-        }
         // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
         // with any invalid sample books what the full sums above contain but the panel must not
         if (team_any<TEAM>(active && !all_ok, bar_id)) {
@@ -595,6 +657,9 @@ static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
 
 template <int N>
 static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *launches) {
+#ifdef E3_DEV_ONLY  // development builds: one instantiation (SASS inspection, quick compiles)
+  return launch_f32<N, 7>(P, st, launches);
+#else
   if (P.noise_mode == 1 && P.noise_gauss) {
     switch (legs) {
       case LEG_NOISE | LEG_THERMAL64: return launch_f32<N, LEG_NOISE | LEG_THERMAL64, true>(P, st, launches);
@@ -615,9 +680,13 @@ static int run_f32_n(const EngineParams &P, int legs, cudaStream_t st, int *laun
   }
   set_error("sds_engine_run: leg mask %d is not instantiated", legs);
   return SDS_ENOTSUP;
+#endif
 }
 
 int run_engine_f32(int N, const EngineParams &P, int legs, cudaStream_t st, int *launches) {
+#ifdef E3_DEV_ONLY
+  return run_f32_n<E3_DEV_ONLY>(P, legs, st, launches);
+#endif
   switch (N) {
     case 64: return run_f32_n<64>(P, legs, st, launches);
     case 128: return run_f32_n<128>(P, legs, st, launches);

@@ -224,6 +224,23 @@ __device__ __forceinline__ f2 lds_f2(uint32_t addr) {
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
+// two packed values in one 128-bit access (16-byte aligned address)
+__device__ __forceinline__ void sts_f2x2(uint32_t addr, f2 v, f2 w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)),
+               "r"((uint32_t)w), "r"((uint32_t)(w >> 32))
+               : "memory");
+}
+__device__ __forceinline__ void lds_f2x2(uint32_t addr, f2 &v, f2 &w) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(w) : "r"(addr) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void sts_f2x2_off(uint32_t addr, f2 v, f2 w) {
+  asm volatile("st.shared.v4.b32 [%0 + %5], {%1, %2, %3, %4};" ::"r"(addr), "r"((uint32_t)v),
+               "r"((uint32_t)(v >> 32)), "r"((uint32_t)w), "r"((uint32_t)(w >> 32)), "n"(OFF)
+               : "memory");
+}
+template <int OFF> __device__ __forceinline__ void lds_f2x2_off(uint32_t addr, f2 &v, f2 &w) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2 + %3];" : "=l"(v), "=l"(w) : "r"(addr), "n"(OFF) : "memory");
+}
 template <int OFF> __device__ __forceinline__ void sts_f2_off(uint32_t addr, f2 v) {
   asm volatile("st.shared.b64 [%0 + %2], %1;" ::"r"(addr), "l"(v), "n"(OFF) : "memory");
 }
@@ -335,6 +352,93 @@ template <int N> struct TeamFftX {
                                              int tau, int bar) {
     const f2 w0[7] = {};
     pass<0, false>(a, a, A, tw, tau, bar, w0);
+  }
+
+  // ---- interleaved pair: the two lockstep transforms share ONE buffer of 16-byte slots -------
+  // Slot j holds (a[j], b[j]), so an exchange access of both transforms is one 128-bit
+  // instruction (half the LDS / STS of run2, the same bytes).  A 128-bit access is served per
+  // quarter warp.  The buffer is PADDED, not XOR-swizzled: slot j sits at j + (j >> 3), which keeps
+  // the eight slots of every quarter warp on distinct 16-byte bank groups for all store and load
+  // patterns of the schedule (N = 64 ... 2048, checked exhaustively) and is ADDITIVE over the
+  // schedule's index split (per-thread part + compile-time part, no carries between them) -- so
+  // every access is [per-thread address + immediate]: no address instruction at all, and no
+  // alignment requirement beyond 16 bytes.  A row's region is IL_BYTES = 18 N bytes.
+  static constexpr int IL_BYTES = 16 * (N + N / 8);
+  static __host__ __device__ constexpr int il_pad(int j) { return j + (j >> 3); }
+  static __device__ __forceinline__ Addr make_addr_il(uint32_t xa, int tau) {
+    Addr A;
+#pragma unroll
+    for (int p = 0; p < NST; ++p) {
+      const int NS = fft_ns(N, p), R = fft_radix(N, p);
+      const int base = (tau / NS) * (NS * R) + (tau % NS);
+      A.st[p] = xa + 16u * (uint32_t)il_pad(base);
+    }
+    A.ld = xa + 16u * (uint32_t)il_pad(tau);
+    return A;
+  }
+  template <int P>
+  static __device__ __forceinline__ void pass_il(f2 (&a)[8], f2 (&b)[8], const Addr &A,
+                                                 const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7]) {
+    constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
+    static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
+    if constexpr (P > 0) {
+#pragma unroll
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+          const f2 w = wp[m * (R - 1) + (q - 1)];
+          a[m + NB * q] = f2_cmul(a[m + NB * q], w);
+          b[m + NB * q] = f2_cmul(b[m + NB * q], w);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+      f2 x[R], y[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        x[q] = a[m + NB * q];
+        y[q] = b[m + NB * q];
+      }
+      RadixP<R>::run(x);
+      RadixP<R>::run(y);
+      if constexpr (P < NPASS - 1) {
+        il_store<P, 0>(A.st[P], x, y);
+      } else {
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          a[m + NB * p] = x[brev(p, LG)];
+          b[m + NB * p] = y[brev(p, LG)];
+        }
+      }
+    }
+    if constexpr (P < NPASS - 1) {
+      f2 wn[7];
+      load_tw<P + 1>(wn, tw, tau);
+      team_sync<WORKER>(bar);
+      il_load<0>(A.ld, a, b);
+      if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
+      pass_il<P + 1>(a, b, A, tw, tau, bar, wn);
+    }
+  }
+  // the eight stores of a radix-8 pass / the eight loads after it, offsets as immediates
+  template <int P, int p>
+  static __device__ __forceinline__ void il_store(uint32_t st, const f2 (&x)[8], const f2 (&y)[8]) {
+    if constexpr (p < 8) {
+      sts_f2x2_off<16 * il_pad(p * fft_ns(N, P))>(st, x[brev(p, 3)], y[brev(p, 3)]);
+      il_store<P, p + 1>(st, x, y);
+    }
+  }
+  template <int r>
+  static __device__ __forceinline__ void il_load(uint32_t ld, f2 (&a)[8], f2 (&b)[8]) {
+    if constexpr (r < 8) {
+      lds_f2x2_off<16 * il_pad(TPR * r)>(ld, a[r], b[r]);
+      il_load<r + 1>(ld, a, b);
+    }
+  }
+  static __device__ __forceinline__ void run2_il(f2 (&a)[8], f2 (&b)[8], const Addr &A,
+                                                 const f2 *__restrict__ tw, int tau, int bar) {
+    const f2 w0[7] = {};
+    pass_il<0>(a, b, A, tw, tau, bar, w0);
   }
 };
 
