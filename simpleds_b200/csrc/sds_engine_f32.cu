@@ -23,6 +23,9 @@ namespace sds {
 #ifndef E3_IL
 #define E3_IL 1  // interleaved 128-bit exchange of the two lockstep transforms
 #endif
+#ifndef E3_TM
+#define E3_TM 1  // last exchange of the lockstep transforms through tensor memory (N = 256)
+#endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
 #endif
@@ -55,6 +58,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // slots with 128-bit accesses (TeamFftX::run2_il): 18 N bytes per row, no alignment requirement;
   // otherwise a pair of XOR-addressed buffers of 8 N bytes, aligned to 8 N
   static constexpr bool IL = E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE);
+  static constexpr bool TM = E3_TM && IL && TeamFftX<N>::TM_OK;
   static constexpr int XROW = IL ? TeamFftX<N>::IL_BYTES : 2 * BUF;  // exchange bytes of one row
   static constexpr int XALIGN = IL ? 128 : BUF;
   static constexpr int XREGION = NWORKER * ROWS * XROW;  // all exchange buffers
@@ -119,7 +123,18 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     for (int i = 0; i < E3_STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // tensor memory for the last exchange: 32 columns per CTA, each warp its own 32 lanes
+  __shared__ uint32_t tm_base_s;
+  if (C::TM && threadIdx.x < 32) tm_alloc32(smem_u32(&tm_base_s));
+  if (C::TM) tm_fence_before();
   __syncthreads();
+  uint32_t tm_a = 0;
+  if (C::TM) {
+    tm_fence_after();
+    tm_a = tm_base_s + ((uint32_t)(threadIdx.x & ~31u) << 16);
+  }
+  // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
+  const int tau_out = C::TM ? FFT::tm_tau(tau) : tau;
 
   // per-thread constants: taper * delta_f at this thread's 8 transform channels
   float tapdf[8];
@@ -276,7 +291,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     }
     for (int step = 0; step < nsteps; ++step) {
       team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
+#ifndef E3_ISSUE_LATE
       if (pleft > 0) issue();
+#endif
       const int i = ci0 + sub;
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
@@ -380,7 +397,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
+        if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
+        else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
 #pragma unroll
@@ -391,6 +409,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       } else {
         FFT::run(vd, fa, tw_s, tau, bar_id);
       }
+#ifdef E3_ISSUE_LATE
+      if (pleft > 0) issue();
+#endif
       if (HAS_D) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -591,7 +612,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int kshift = (tau + TPR * r + N / 2) % N;
+      const int kshift = (tau_out + TPR * r + N / 2) % N;
       float s2 = S2[r], sn2 = Sn2[r];
 #pragma unroll
       for (int off = TPR; off < 32; off <<= 1) {
@@ -625,6 +646,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
     }
   }
+  if (C::TM) {
+    tm_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tm_dealloc32(tm_base_s);
+  }
 }
 
 template <int N, int LEGS, bool GAUSS = false>
@@ -649,6 +675,11 @@ static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
     set_error("sds_engine_run: kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
   }
+  // the occupancy query answers 1 for a kernel that allocates tensor memory, whatever it allocates;
+  // three CTAs with 32 of the 512 columns each are resident together (scripts/ubench/tmem_xchg.cu), and
+  // registers and shared memory are budgeted for MINB (the work queue is dynamic: a CTA that had to wait
+  // for an SM would still be correct)
+  if (C::TM && per_sm < C::MINB) per_sm = C::MINB;
   engine_f32_kernel<N, LEGS, GAUSS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
   SDS_LAUNCH_CHECK("engine_f32_kernel");
   ++*launches;

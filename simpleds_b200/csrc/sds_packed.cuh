@@ -250,6 +250,48 @@ template <int OFF> __device__ __forceinline__ f2 lds_f2_off(uint32_t addr) {
   return v;
 }
 
+// ---- tensor memory (TMEM) as an exchange medium between the threads of a warp ------------------
+// tcgen05.st.32x32b writes thread t's registers to TMEM lane t; tcgen05.ld.16x256b reads the
+// accumulator-fragment layout (thread t <- lanes t/4 and t/4 + 8, column pairs t%4 + 4j).  Store with
+// the one, load with the other, and (thread, register) index bits are swapped -- the exchange an FFT
+// pass needs -- without one wavefront of the shared-memory data pipe (which bounds the fused engine)
+// and beside it: scripts/ubench/tmem_xchg.cu measures 14 clk per 4 KB warp exchange and SM against
+// 32 clk through shared memory, and the two overlap (profiles/r2_tmem_exchange_microbench.txt).
+__device__ __forceinline__ void tm_alloc32(uint32_t smem_dst) {  // one warp; 32 columns
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_dst) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc32(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// thread t -> lane t, columns [col, col + 16): eight packed values
+__device__ __forceinline__ void tm_st8(uint32_t addr, f2 v0, f2 v1, f2 v2, f2 v3, f2 v4, f2 v5, f2 v6, f2 v7) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr),
+      "r"((uint32_t)v0), "r"((uint32_t)(v0 >> 32)), "r"((uint32_t)v1), "r"((uint32_t)(v1 >> 32)), "r"((uint32_t)v2),
+      "r"((uint32_t)(v2 >> 32)), "r"((uint32_t)v3), "r"((uint32_t)(v3 >> 32)), "r"((uint32_t)v4), "r"((uint32_t)(v4 >> 32)),
+      "r"((uint32_t)v5), "r"((uint32_t)(v5 >> 32)), "r"((uint32_t)v6), "r"((uint32_t)(v6 >> 32)), "r"((uint32_t)v7),
+      "r"((uint32_t)(v7 >> 32))
+      : "memory");
+}
+// 16 lanes from the address's lane, 16 columns: thread t gets, as packed values,
+//   d0 = (lane t/4, pair t%4), d1 = (lane t/4 + 8, pair t%4), d2 = (lane t/4, pair 4 + t%4), d3 = (lane t/4 + 8, pair 4 + t%4)
+__device__ __forceinline__ void tm_ld4(uint32_t addr, f2 &d0, f2 &d1, f2 &d2, f2 &d3) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr)
+               : "memory");
+  d0 = (f2)r[0] | ((f2)r[1] << 32);
+  d1 = (f2)r[2] | ((f2)r[3] << 32);
+  d2 = (f2)r[4] | ((f2)r[5] << 32);
+  d3 = (f2)r[6] | ((f2)r[7] << 32);
+}
+
 template <int N> struct TeamFftX {
   static constexpr int TPR = N / 8;
   static constexpr int NPASS = fft_npass(N);
@@ -376,9 +418,18 @@ template <int N> struct TeamFftX {
     A.ld = xa + 16u * (uint32_t)il_pad(tau);
     return A;
   }
-  template <int P>
+  // TM: the LAST exchange goes through tensor memory instead (one-warp teams whose last pass has radix
+  // 4, i.e. N = 256).  In the Stockham schedule that exchange sends output t of thread tau to thread
+  // (t1 t0 tau2 tau1 tau0), slot (tau4 tau3 t2) [index bits]; the TMEM store / load pair sends it to
+  // thread (tau2 tau1 tau0 t1 t0), slot (tau4 t2 tau3): the same exchange up to a fixed renaming.  So
+  // after it physical lane l ACTS AS team member tm_tau(l) (twiddle lookups of the last pass, ownership
+  // of the spectrum: bins tm_tau(l) + TPR r) and the loaded slots are renamed (low two bits swapped).
+  static constexpr bool TM_OK = NPASS >= 2 && fft_radix(N, NPASS - 1) == 4 && TPR == 32;
+  static __device__ __forceinline__ int tm_tau(int lane) { return ((lane & 3) << 3) | (lane >> 2); }
+  template <int P, bool TM = false>
   static __device__ __forceinline__ void pass_il(f2 (&a)[8], f2 (&b)[8], const Addr &A,
-                                                 const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7]) {
+                                                 const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7],
+                                                 uint32_t tm = 0) {
     constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
     static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
     if constexpr (P > 0) {
@@ -401,7 +452,13 @@ template <int N> struct TeamFftX {
       }
       RadixP<R>::run(x);
       RadixP<R>::run(y);
-      if constexpr (P < NPASS - 1) {
+      if constexpr (TM && P == NPASS - 2) {
+        // data in columns [0, 16), noise in [16, 32) of the warp's 32 lanes
+        tm_st8(tm, x[brev(0, 3)], x[brev(1, 3)], x[brev(2, 3)], x[brev(3, 3)], x[brev(4, 3)], x[brev(5, 3)],
+               x[brev(6, 3)], x[brev(7, 3)]);
+        tm_st8(tm + 16u, y[brev(0, 3)], y[brev(1, 3)], y[brev(2, 3)], y[brev(3, 3)], y[brev(4, 3)], y[brev(5, 3)],
+               y[brev(6, 3)], y[brev(7, 3)]);
+      } else if constexpr (P < NPASS - 1) {
         il_store<P, 0>(A.st[P], x, y);
       } else {
 #pragma unroll
@@ -411,13 +468,26 @@ template <int N> struct TeamFftX {
         }
       }
     }
-    if constexpr (P < NPASS - 1) {
+    if constexpr (TM && P == NPASS - 2) {
+      f2 wn[7];
+      load_tw<P + 1>(wn, tw, tm_tau(tau));
+#ifndef SDS_TM_NOWAIT
+      tm_wait_st();
+#endif
+      // loaded slot (tau4 t2 tau3) is logical slot (tau4 tau3 t2): 1 <-> 2, 5 <-> 6
+      tm_ld4(tm, a[0], a[2], a[1], a[3]);
+      tm_ld4(tm + (16u << 16), a[4], a[6], a[5], a[7]);
+      tm_ld4(tm + 16u, b[0], b[2], b[1], b[3]);
+      tm_ld4(tm + (16u << 16) + 16u, b[4], b[6], b[5], b[7]);
+      tm_wait_ld();
+      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm);
+    } else if constexpr (P < NPASS - 1) {
       f2 wn[7];
       load_tw<P + 1>(wn, tw, tau);
       team_sync<WORKER>(bar);
       il_load<0>(A.ld, a, b);
       if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
-      pass_il<P + 1>(a, b, A, tw, tau, bar, wn);
+      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm);
     }
   }
   // the eight stores of a radix-8 pass / the eight loads after it, offsets as immediates
@@ -439,6 +509,13 @@ template <int N> struct TeamFftX {
                                                  const f2 *__restrict__ tw, int tau, int bar) {
     const f2 w0[7] = {};
     pass_il<0>(a, b, A, tw, tau, bar, w0);
+  }
+  // tm: the warp's tensor-memory address (its 32 lanes, 32 columns); spectrum bins of lane l on return:
+  // tm_tau(l) + TPR r
+  static __device__ __forceinline__ void run2_tm(f2 (&a)[8], f2 (&b)[8], const Addr &A,
+                                                 const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
+    const f2 w0[7] = {};
+    pass_il<0, true>(a, b, A, tw, tau, bar, w0, tm);
   }
 };
 
