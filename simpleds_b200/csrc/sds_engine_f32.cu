@@ -26,6 +26,9 @@ namespace sds {
 #ifndef E3_TM
 #define E3_TM 1  // last exchange of the lockstep transforms through tensor memory (N = 256)
 #endif
+#ifndef E3_TACC
+#define E3_TACC 1  // accumulators in tensor memory: 128 registers, 16 warps per SM (N = 256, three legs)
+#endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
 #endif
@@ -48,7 +51,14 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   static constexpr int NWORKER = THREADS / TEAM;
   // resident CTAs per SM the register allocation aims at (12 warps: measured best at N = 256)
   // (N = 2048 runs 256-thread CTAs: a second one would halve their registers -- measured slower)
-  static constexpr int WARPS_PER_SM = (NOISE_ONLY && THREADS <= 128) ? 16 : E3_WARPS_PER_SM;
+  // TACC: every per-item accumulator (pair sums, |x|^2 sums, thermal sums, the per-time |S1|^2 sums) lives
+  // in thread-private tensor-memory columns and is read-modified-written once per row with one
+  // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
+  static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && LEGS == (LEG_DATA | LEG_NOISE | LEG_THERMAL) && !GAUSS &&
+                               N == 256;
+  static constexpr int STAGES = TACC ? 2 : E3_STAGES;
+  static constexpr int TM_COLS = TACC ? 128 : 32;
+  static constexpr int WARPS_PER_SM = (TACC || (NOISE_ONLY && THREADS <= 128)) ? 16 : E3_WARPS_PER_SM;
   static constexpr int MINB = (WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (WARPS_PER_SM * 32) / THREADS;
   static constexpr int VISB = (LEGS & LEG_DATA) ? 8 * N : 0;
   static constexpr int ROWB = VISB + 5 * N;             // vis 8N (data leg only) | nsample 4N | flags N
@@ -65,7 +75,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
   static constexpr int HEAD = 192;
-  static constexpr int WORKER_BYTES = HEAD + E3_STAGES * SLOT + 8 * N;
+  static constexpr int WORKER_BYTES = HEAD + STAGES * SLOT + (TACC ? 0 : 8 * N);
   // XALIGN bytes of slack in front: the exchange region is aligned at run time
   static constexpr int SMEM = XALIGN + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
@@ -117,21 +127,29 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t tv_a = wb_a + 64;  // [32] floats: integration times of the next steps
   const uint32_t full_a = wb_a, stages_a = wb_a + C::HEAD;  // shared-space addresses
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
-  float *pw_s = reinterpret_cast<float *>(stages + E3_STAGES * C::SLOT);
-  for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
+  float *pw_s = reinterpret_cast<float *>(stages + C::STAGES * C::SLOT);
+  if (!C::TACC)
+    for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
-    for (int i = 0; i < E3_STAGES; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // tensor memory for the last exchange: 32 columns per CTA, each warp its own 32 lanes
   __shared__ uint32_t tm_base_s;
-  if (C::TM && threadIdx.x < 32) tm_alloc32(smem_u32(&tm_base_s));
+  if (C::TM && threadIdx.x < 32) tm_alloc<C::TM_COLS>(smem_u32(&tm_base_s));
   if (C::TM) tm_fence_before();
   __syncthreads();
   uint32_t tm_a = 0;
   if (C::TM) {
     tm_fence_after();
     tm_a = tm_base_s + ((uint32_t)(threadIdx.x & ~31u) << 16);
+  }
+  // tensor-memory columns of the accumulators (TACC), after the 32 columns of the exchange:
+  // [32, 64) S1, Sn1 | [64, 80) S2, Sn2 | [80, 104) tA, tB, tC | [104, 120) per-time |S1|^2 sums
+  constexpr uint32_t TC_S1 = 32, TC_S2 = 64, TC_T = 80, TC_PW = 104;
+  if (C::TACC) {
+    const uint32_t z16[16] = {};
+    tm_st_w16(tm_a + TC_PW, z16);
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
   const int tau_out = C::TM ? FFT::tm_tau(tau) : tau;
@@ -199,7 +217,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           tma_load_1d_a(dst + C::VISB + 4 * N, P.flags + e, N, bar);
         }
       }
-      slot_p = slot_p + 1 == E3_STAGES ? 0 : slot_p + 1;
+      slot_p = slot_p + 1 == C::STAGES ? 0 : slot_p + 1;
       pi0 += ROWS;
       pe += ROWS * row_stride;
       if (pi0 >= ng) {
@@ -246,6 +264,16 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
 #pragma unroll
     for (int r = 0; r < 8; ++r) dA[r] = dB[r] = dC[r] = 0.0;
+    if constexpr (C::TACC) {  // the item's accumulators start at zero in tensor memory
+      const uint32_t z32[32] = {};
+      const uint32_t z16[16] = {};
+      const uint32_t z8[8] = {};
+      tm_st_w32(tm_a + TC_S1, z32);
+      tm_st_w16(tm_a + TC_S2, z16);
+      tm_st_w16(tm_a + TC_T, z16);
+      tm_st_w8(tm_a + TC_T + 16, z8);
+      tm_wait_st();
+    }
 
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
@@ -261,7 +289,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     u32x4 nwords = {0u, 0u, 0u, 0u};
     const uint64_t nblk = (uint64_t)((P.nbl_total + 3) >> 2);
     const uint64_t blk_sp = (uint64_t)((int64_t)s * P.npol + p) * nblk;
-    for (int k = 0; k < E3_STAGES - 1 && pleft > 0; ++k) issue();
+    for (int k = 0; k < C::STAGES - 1 && pleft > 0; ++k) issue();
     // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
     // on the critical path of every row)
     float tint_next = 1.f;
@@ -386,6 +414,19 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_T) {  // thermal sums first: nsample^-1/2 is dead before the transforms start
         const f2 it2 = f2_make(itv, itv);
+        if constexpr (C::TACC) {
+          // (the stores of the previous row were fenced by its exchange)
+          uint32_t w16[16], w8[8];
+          tm_ld_w16(tm_a + TC_T, w16);
+          tm_ld_w8(tm_a + TC_T + 16, w8);
+          tm_wait_ld();
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            tA[m] = f2_from_words(w16[2 * m], w16[2 * m + 1]);
+            tB[m] = f2_from_words(w16[8 + 2 * m], w16[8 + 2 * m + 1]);
+            tC[m] = f2_from_words(w8[2 * m], w8[2 * m + 1]);
+          }
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const f2 aa = f2_make(av[2 * m], av[2 * m + 1]);
@@ -394,6 +435,17 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           tB[m] = f2_add(tB[m], ab);
           tC[m] = f2_fma(aa, ab, tC[m]);
         }
+        if constexpr (C::TACC) {
+          uint32_t w16[16], w8[8];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            w16[2 * m] = (uint32_t)tA[m]; w16[2 * m + 1] = (uint32_t)(tA[m] >> 32);
+            w16[8 + 2 * m] = (uint32_t)tB[m]; w16[8 + 2 * m + 1] = (uint32_t)(tB[m] >> 32);
+            w8[2 * m] = (uint32_t)tC[m]; w8[2 * m + 1] = (uint32_t)(tC[m] >> 32);
+          }
+          tm_st_w16(tm_a + TC_T, w16);
+          tm_st_w8(tm_a + TC_T + 16, w8);
+        }
       }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
@@ -401,6 +453,20 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
+        if constexpr (C::TACC) {
+          // (the exchange inside the transforms fenced the stores of the previous row)
+          uint32_t w32[32], w16[16];
+          tm_ld_w32(tm_a + TC_S1, w32);
+          tm_ld_w16(tm_a + TC_S2, w16);
+          tm_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            S1[r] = f2_from_words(w32[2 * r], w32[2 * r + 1]);
+            Sn1[r] = f2_from_words(w32[16 + 2 * r], w32[16 + 2 * r + 1]);
+            S2[r] = __uint_as_float(w16[r]);
+            Sn2[r] = __uint_as_float(w16[8 + r]);
+          }
+        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           Sn1[r] = f2_add(Sn1[r], vn[r]);
@@ -418,6 +484,30 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           S1[r] = f2_add(S1[r], vd[r]);
           S2[r] = fmaf(f2_lo(vd[r]), f2_lo(vd[r]), fmaf(f2_hi(vd[r]), f2_hi(vd[r]), S2[r]));
         }
+      }
+      if constexpr (C::TACC) {
+        if (ci0 + ROWS >= ng) {  // the time closes with this row: P += |sum over the group's rows|^2
+          uint32_t pw[16];
+          tm_ld_w16(tm_a + TC_PW, pw);
+          tm_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            pw[r] = __float_as_uint(__uint_as_float(pw[r]) + f2_hsum(f2_mul(S1[r], S1[r])));
+            pw[8 + r] = __float_as_uint(__uint_as_float(pw[8 + r]) + f2_hsum(f2_mul(Sn1[r], Sn1[r])));
+            S1[r] = Sn1[r] = 0ull;
+          }
+          tm_st_w16(tm_a + TC_PW, pw);
+        }
+        uint32_t w32[32], w16[16];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          w32[2 * r] = (uint32_t)S1[r]; w32[2 * r + 1] = (uint32_t)(S1[r] >> 32);
+          w32[16 + 2 * r] = (uint32_t)Sn1[r]; w32[16 + 2 * r + 1] = (uint32_t)(Sn1[r] >> 32);
+          w16[r] = __float_as_uint(S2[r]);
+          w16[8 + r] = __float_as_uint(Sn2[r]);
+        }
+        tm_st_w32(tm_a + TC_S1, w32);
+        tm_st_w16(tm_a + TC_S2, w16);
       }
 
       if (HAS_T) {
@@ -483,7 +573,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
 
       // ---- advance the consumer; close the time when its last row is done -----------
-      slot_c = slot_c + 1 == E3_STAGES ? 0 : slot_c + 1;
+      slot_c = slot_c + 1 == C::STAGES ? 0 : slot_c + 1;
       if (slot_c == 0) par_c ^= 1u;
       ci0 += ROWS;
       if (ci0 >= ng) {
@@ -492,7 +582,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         ++it_off;
         ++rid_t;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {  // P += |sum over the group's rows|^2
+        for (int r = 0; r < 8 && !C::TACC; ++r) {  // P += |sum over the group's rows|^2
           f2 sd = S1[r], sn = Sn1[r];
 #pragma unroll
           for (int off = TPR; off < 32; off <<= 1) {
@@ -513,6 +603,22 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           // row's exchange buffers ((A, B) pairs in the first, C in the second)
           team_sync<TEAM>(bar_id);  // the step's last transform reads are done
           float Ar[8], Br[8], Cr[8], Ap[8], Bp[8], Cp[8];
+          if constexpr (C::TACC) {  // (stored before this row's exchange, which fenced them)
+            uint32_t w16[16], w8[8];
+            tm_ld_w16(tm_a + TC_T, w16);
+            tm_ld_w8(tm_a + TC_T + 16, w8);
+            tm_wait_ld();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              tA[m] = f2_from_words(w16[2 * m], w16[2 * m + 1]);
+              tB[m] = f2_from_words(w16[8 + 2 * m], w16[8 + 2 * m + 1]);
+              tC[m] = f2_from_words(w8[2 * m], w8[2 * m + 1]);
+            }
+            const uint32_t z16[16] = {};
+            const uint32_t z8[8] = {};
+            tm_st_w16(tm_a + TC_T, z16);
+            tm_st_w8(tm_a + TC_T + 16, z8);
+          }
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             Ar[2 * m] = f2_lo(tA[m]); Ar[2 * m + 1] = f2_hi(tA[m]);
@@ -610,6 +716,21 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     }
 
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
+    uint32_t pwt[16];
+    if constexpr (C::TACC) {
+      uint32_t w16[16];
+      tm_wait_st();
+      tm_ld_w16(tm_a + TC_S2, w16);
+      tm_ld_w16(tm_a + TC_PW, pwt);
+      tm_wait_ld();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        S2[r] = __uint_as_float(w16[r]);
+        Sn2[r] = __uint_as_float(w16[8 + r]);
+      }
+      const uint32_t z16[16] = {};
+      tm_st_w16(tm_a + TC_PW, z16);
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int kshift = (tau_out + TPR * r + N / 2) % N;
@@ -621,14 +742,14 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (sub == 0) {
         if (HAS_D) {
-          atomicAdd(P.pow_all + obase + kshift, (double)pw_s[tau + TPR * r]);
+          atomicAdd(P.pow_all + obase + kshift, (double)(C::TACC ? __uint_as_float(pwt[r]) : pw_s[tau + TPR * r]));
           atomicAdd(P.pow_auto + obase + kshift, (double)s2);
-          pw_s[tau + TPR * r] = 0.f;
+          if (!C::TACC) pw_s[tau + TPR * r] = 0.f;
         }
         if (HAS_N) {
-          atomicAdd(P.noise_all + obase + kshift, (double)pw_s[N + tau + TPR * r]);
+          atomicAdd(P.noise_all + obase + kshift, (double)(C::TACC ? __uint_as_float(pwt[8 + r]) : pw_s[N + tau + TPR * r]));
           atomicAdd(P.noise_auto + obase + kshift, (double)sn2);
-          pw_s[N + tau + TPR * r] = 0.f;
+          if (!C::TACC) pw_s[N + tau + TPR * r] = 0.f;
         }
       }
     }
@@ -649,7 +770,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   if (C::TM) {
     tm_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tm_dealloc32(tm_base_s);
+    if (threadIdx.x < 32) tm_dealloc<C::TM_COLS>(tm_base_s);
   }
 }
 
