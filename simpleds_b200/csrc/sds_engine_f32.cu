@@ -29,6 +29,9 @@ namespace sds {
 #ifndef E3_TACC
 #define E3_TACC 1  // accumulators in tensor memory: 128 registers, 16 warps per SM (N = 256, three legs)
 #endif
+#ifndef E3_F4
+#define E3_F4 1  // N = 2048: one team-wide exchange, then one 256-point transform per warp (TeamFft8x256)
+#endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
 #endif
@@ -55,9 +58,12 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // in thread-private tensor-memory columns and is read-modified-written once per row with one
   // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
   static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && LEGS == (LEG_DATA | LEG_NOISE | LEG_THERMAL) && !GAUSS &&
-                               N == 256;
+                               (N == 256 || (E3_F4 && N == 2048));
   static constexpr int STAGES = TACC ? 2 : E3_STAGES;
-  static constexpr int TM_COLS = TACC ? 128 : 32;
+  // tensor-memory columns of one warp (exchange 32 + accumulators 88), and of the CTA: warps w and w + 4
+  // share TMEM lanes, so every set of four warps has its own column range
+  static constexpr int TM_WCOLS = TACC ? 128 : 32;
+  static constexpr int TM_COLS = TM_WCOLS * (THREADS / 128);
   static constexpr int WARPS_PER_SM = (TACC || (NOISE_ONLY && THREADS <= 128)) ? 16 : E3_WARPS_PER_SM;
   static constexpr int MINB = (WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (WARPS_PER_SM * 32) / THREADS;
   static constexpr int VISB = (LEGS & LEG_DATA) ? 8 * N : 0;
@@ -68,11 +74,14 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // slots with 128-bit accesses (TeamFftX::run2_il): 18 N bytes per row, no alignment requirement;
   // otherwise a pair of XOR-addressed buffers of 8 N bytes, aligned to 8 N
   static constexpr bool IL = E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE);
-  static constexpr bool TM = E3_TM && IL && TeamFftX<N>::TM_OK;
+  static constexpr bool F4 = E3_F4 && E3_TM && IL && N == 2048;
+  static constexpr bool TM = E3_TM && IL && (TeamFftX<N>::TM_OK || F4);
   static constexpr int XROW = IL ? TeamFftX<N>::IL_BYTES : 2 * BUF;  // exchange bytes of one row
   static constexpr int XALIGN = IL ? 128 : BUF;
   static constexpr int XREGION = NWORKER * ROWS * XROW;  // all exchange buffers
-  static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
+  static constexpr int TW_ENTRIES = (E3_F4 && E3_TM && E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE) && N == 2048)
+                                        ? TeamFft8x256::TW_TOTAL : fft_tw_total(N);
+  static constexpr int TW_BYTES = ((TW_ENTRIES * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
   static constexpr int HEAD = 192;
   static constexpr int WORKER_BYTES = HEAD + STAGES * SLOT + (TACC ? 0 : 8 * N);
@@ -111,8 +120,12 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   asm volatile("" : "+r"(sb_a));
 #endif
   f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
-  for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
-    tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
+  if constexpr (C::F4) {
+    TeamFft8x256::fill_tables(tw_s, threadIdx.x, C::THREADS);
+  } else {
+    for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
+      tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
+  }
   // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
   uint32_t xa = sb_a + (uint32_t)(wid * ROWS + sub) * C::XROW;
   uint32_t wb_a = sb_a + C::XREGION + C::TW_BYTES + (uint32_t)wid * C::WORKER_BYTES;
@@ -121,6 +134,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   asm volatile("" : "+r"(wb_a));
 #endif
   const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : FFT::make_addr(xa, tau);
+  // four-step: the addresses of the warp-local 256-point transform in the warp's region of the row's buffer
+  const typename TeamFftX<256>::Addr fa4 =
+      TeamFftX<256>::make_addr_il(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION, tau & 31);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(__cvta_shared_to_generic(wb_a));
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + C::HEAD;
@@ -142,7 +158,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   uint32_t tm_a = 0;
   if (C::TM) {
     tm_fence_after();
-    tm_a = tm_base_s + ((uint32_t)(threadIdx.x & ~31u) << 16);
+    const uint32_t warp = threadIdx.x >> 5;
+    tm_a = tm_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)C::TM_WCOLS;
   }
   // tensor-memory columns of the accumulators (TACC), after the 32 columns of the exchange:
   // [32, 64) S1, Sn1 | [64, 80) S2, Sn2 | [80, 104) tA, tB, tC | [104, 120) per-time |S1|^2 sums
@@ -152,7 +169,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     tm_st_w16(tm_a + TC_PW, z16);
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
-  const int tau_out = C::TM ? FFT::tm_tau(tau) : tau;
+  const int tau_out = C::F4 ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31) : C::TM ? FFT::tm_tau(tau) : tau;
 
   // per-thread constants: taper * delta_f at this thread's 8 transform channels
   float tapdf[8];
@@ -449,7 +466,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       }
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
+        if constexpr (C::F4) TeamFft8x256::run2(vd, vn, xa, fa4, tw_s, tau, bar_id, tm_a);
+        else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else FFT::run(vn, fa, tw_s, tau, bar_id);

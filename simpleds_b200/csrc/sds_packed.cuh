@@ -557,6 +557,78 @@ template <int N> struct TeamFftX {
   }
 };
 
+// ---- N = 2048 = 8 x 256, "four-step" -------------------------------------------------------------
+// The generic schedule runs a long row on a 256-thread team with a team-wide barrier per pass (three
+// of them at N = 2048).  Here the team makes ONE radix-8 pass (thread tau holds x[tau + 256 r]) and ONE
+// team-wide exchange -- a transposition after which warp w owns the 256 samples of residue k1 = w --
+// and then every warp runs its own 256-point transform on the warp-local machinery above (interleaved
+// exchange in the warp's region of the same buffer, tensor memory for the last exchange), with no
+// further team barrier:   X[k1 + 8 k2] = sum_n2 W_256^(n2 k2) [ W_2048^(n2 k1) sum_r x[n2 + 256 r] W_8^(r k1) ].
+// On return lane l of warp w holds bins  w + 8 (tm_tau(l) + 32 r).
+struct TeamFft8x256 {
+  using F256 = TeamFftX<256>;
+  static constexpr int N = 2048;
+  static constexpr int REGION = F256::IL_BYTES;            // 4608 B: one warp's padded exchange region
+  static constexpr int XBYTES = 8 * REGION;                // the row's exchange bytes (= 18 N)
+  static constexpr int TW_A = 2048;                        // [k1][n2] W_2048^(n2 k1)
+  static constexpr int TW_TOTAL = TW_A + fft_tw_total(256);  // + the team table of length 256
+  // tables computed by the CTA itself (sincospi of exact arguments), no plan storage
+  static __device__ __forceinline__ void fill_tables(f2 *tab, int tid, int nthreads) {
+    for (int i = tid; i < TW_A; i += nthreads) {
+      const int k1 = i >> 8, n2 = i & 255;
+      float sn, cs;
+      sincospif(-2.0f * (float)((n2 * k1) & 2047) / 2048.0f, &sn, &cs);
+      tab[i] = f2_make(cs, sn);
+    }
+    constexpr int NP = fft_npass(256);
+#pragma unroll
+    for (int p = 1; p < NP; ++p) {
+      const int R = fft_radix(256, p), NB = 8 / R, NS = fft_ns(256, p), off = fft_tw_offset(256, p);
+      for (int i = tid; i < NB * (R - 1) * 32; i += nthreads) {
+        const int tau = i & 31, mq = i >> 5, m = mq / (R - 1), q = mq % (R - 1) + 1;
+        const int k = (tau + 32 * m) % NS;
+        float sn, cs;
+        sincospif(-2.0f * (float)(q * k) / (float)(NS * R), &sn, &cs);
+        tab[TW_A + off + i] = f2_make(cs, sn);
+      }
+    }
+  }
+  template <int k1>
+  static __device__ __forceinline__ void store_t(uint32_t st, const f2 (&a)[8], const f2 (&b)[8]) {
+    if constexpr (k1 < 8) {
+      sts_f2x2_off<k1 * REGION>(st, a[brev(k1, 3)], b[brev(k1, 3)]);
+      store_t<k1 + 1>(st, a, b);
+    }
+  }
+  template <int r>
+  static __device__ __forceinline__ void load_t(uint32_t ld, f2 (&a)[8], f2 (&b)[8]) {
+    if constexpr (r < 8) {
+      lds_f2x2_off<512 * r>(ld, a[r], b[r]);
+      load_t<r + 1>(ld, a, b);
+    }
+  }
+  // xT: the row's exchange buffer; A: make_addr_il(xT + (tau >> 5) REGION, tau & 31); tw: the tables above
+  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], uint32_t xT, const typename F256::Addr &A,
+                                              const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
+    RadixP<8>::run(a);
+    RadixP<8>::run(b);
+    store_t<0>(xT + 16u * (uint32_t)tau, a, b);
+    const int w = tau >> 5, lane = tau & 31;
+    f2 t[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t[r] = tw[w * 256 + lane + 32 * r];
+    team_sync<256>(bar);
+    load_t<0>(xT + (uint32_t)w * REGION + 16u * (uint32_t)lane, a, b);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a[r] = f2_cmul(a[r], t[r]);
+      b[r] = f2_cmul(b[r], t[r]);
+    }
+    __syncwarp();  // the warp has read its region; its own exchange may overwrite it
+    F256::run2_tm(a, b, A, tw + TW_A, lane, bar, tm);
+  }
+};
+
 // ---- small helpers shared by the fused engines ------------------------------------------------
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
