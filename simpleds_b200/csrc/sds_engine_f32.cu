@@ -142,12 +142,15 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   unsigned char *stages = wbase + C::HEAD;
   const uint32_t tv_a = wb_a + 64;  // [32] floats: integration times of the next steps
   const uint32_t full_a = wb_a, stages_a = wb_a + C::HEAD;  // shared-space addresses
+  const uint32_t free_a = wb_a + 32;  // four-step: the buffer-release barrier
+  uint32_t par_f = 1u;                // its phase parity (a fresh barrier passes a wait on parity 1)
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
   float *pw_s = reinterpret_cast<float *>(stages + C::STAGES * C::SLOT);
   if (!C::TACC)
     for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1);
+    if (C::F4) mbar_init(&full[4], TEAM / 32);  // four-step: "the team's exchange buffer is free" (one arrival per warp)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // tensor memory for the last exchange: 32 columns per CTA, each warp its own 32 lanes
@@ -270,7 +273,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     float dfc[48];
     double dA[8], dB[8], dC[8];  // T64: the same sums per channel tau + TPR r in fp64
     double ddfc[T64 ? 48 : 1];
-    bool dirty_time = false;
+    bool dirty_time = false, dirty_row = false;
     double th_all_acc = 0.0, th_auto_acc = 0.0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -306,7 +309,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     u32x4 nwords = {0u, 0u, 0u, 0u};
     const uint64_t nblk = (uint64_t)((P.nbl_total + 3) >> 2);
     const uint64_t blk_sp = (uint64_t)((int64_t)s * P.npol + p) * nblk;
-    for (int k = 0; k < C::STAGES - 1 && pleft > 0; ++k) issue();
+    // (four-step: a row's slot is refilled from the MIDDLE of the step that consumed it, so every slot is in flight)
+    for (int k = 0; k < C::STAGES - (C::F4 ? 0 : 1) && pleft > 0; ++k) issue();
     // integration time of the step's row, loaded one step ahead (an L2 round trip otherwise sits
     // on the critical path of every row)
     float tint_next = 1.f;
@@ -333,12 +337,15 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     if (TV) {
       team_sync<TEAM>(bar_id);  // the previous item's last reads of the ring are done
       if ((threadIdx.x & 16u) == 0) tv_fill((int)(threadIdx.x & 15u));
+      if (C::F4) team_sync<TEAM>(bar_id);  // (the other schedules sync at the top of every step)
     }
     for (int step = 0; step < nsteps; ++step) {
-      team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
+      if (!C::F4) {
+        team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
 #ifndef E3_ISSUE_LATE
-      if (pleft > 0) issue();
+        if (pleft > 0) issue();
 #endif
+      }
       const int i = ci0 + sub;
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
@@ -464,10 +471,46 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           tm_st_w8(tm_a + TC_T + 16, w8);
         }
       }
+      // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
+      // with any invalid sample books what the full sums above contain but the panel must not
+      auto book_deficits = [&]() {
+        if (!dirty_time) {
+#pragma unroll 1
+          for (int k = 0; k < 48; ++k) dfc[k] = 0.f;
+          dirty_time = true;
+        }
+        if (active) {
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            const int c = tau + TPR * q;
+            if (c + 1 >= N) continue;
+            const float nl = ns_s[TPR * q], nr = ns_s[TPR * q + 1];
+            if ((nl > 0.f) == (nr > 0.f)) continue;
+            const float a1 = fast_rsqrt(nl > 0.f ? nl : nr);
+            float *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
+            d[0] += a1;
+            d[1] += a1 * itv;
+            d[2] += a1 * a1 * itv;
+          }
+        }
+      };
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
-        if constexpr (C::F4) TeamFft8x256::run2(vd, vn, xa, fa4, tw_s, tau, bar_id, tm_a);
-        else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
+        if constexpr (C::F4) {
+          TeamFft8x256::front(vd, vn);
+          mbar_wait_a(free_a, par_f);  // every warp has made its last read of the previous row's buffer
+          par_f ^= 1u;
+          TeamFft8x256::store(vd, vn, xa, tau);
+          // the row's ONE team-wide barrier, carrying the "some sample of the row is invalid" vote
+          dirty_row = team_any<TEAM>(active && !all_ok, bar_id);
+          if (HAS_T && dirty_row) {  // rare: the booking re-reads nsample of the staged row
+            book_deficits();
+            team_sync<TEAM>(bar_id);
+          }
+          // all warps have consumed this row's slot: refill it (two rows ahead)
+          if (pleft > 0) issue();
+          TeamFft8x256::back(vd, vn, xa, fa4, tw_s, tau, bar_id, tm_a, free_a);
+        } else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
@@ -528,30 +571,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         tm_st_w16(tm_a + TC_S2, w16);
       }
 
-      if (HAS_T) {
-        // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
-        // with any invalid sample books what the full sums above contain but the panel must not
-        if (team_any<TEAM>(active && !all_ok, bar_id)) {
-          if (!dirty_time) {
-#pragma unroll 1
-            for (int k = 0; k < 48; ++k) dfc[k] = 0.f;
-            dirty_time = true;
-          }
-          if (active) {
-#pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-              const int c = tau + TPR * q;
-              if (c + 1 >= N) continue;
-              const float nl = ns_s[TPR * q], nr = ns_s[TPR * q + 1];
-              if ((nl > 0.f) == (nr > 0.f)) continue;
-              const float a1 = fast_rsqrt(nl > 0.f ? nl : nr);
-              float *d = dfc + 6 * q + (nl > 0.f ? 0 : 3);
-              d[0] += a1;
-              d[1] += a1 * itv;
-              d[2] += a1 * a1 * itv;
-            }
-          }
-        }
+      if (HAS_T && !C::F4) {
+        if (team_any<TEAM>(active && !all_ok, bar_id)) book_deficits();
       }
 
       if (T64) {
@@ -659,6 +680,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
               Ap[r] = Bp[r] = Cp[r] = 0.f;
             }
           }
+          // four-step: the next row's transposed stores are gated by the buffer-release barrier, which does
+          // not know about these reads
+          if (C::F4) team_sync<TEAM>(bar_id);
           if (dirty_time) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {

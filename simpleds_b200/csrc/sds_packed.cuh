@@ -464,10 +464,12 @@ template <int N> struct TeamFftX {
   // of the spectrum: bins tm_tau(l) + TPR r) and the loaded slots are renamed (low two bits swapped).
   static constexpr bool TM_OK = NPASS >= 2 && fft_radix(N, NPASS - 1) == 4 && TPR == 32;
   static __device__ __forceinline__ int tm_tau(int lane) { return ((lane & 3) << 3) | (lane >> 2); }
+  // free_bar (TM only): an mbarrier on which lane 0 arrives once the warp has made its last read of the
+  // exchange region (the four-step schedule lets the team overwrite the region as soon as all warps have)
   template <int P, bool TM = false>
   static __device__ __forceinline__ void pass_il(f2 (&a)[8], f2 (&b)[8], const Addr &A,
                                                  const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7],
-                                                 uint32_t tm = 0) {
+                                                 uint32_t tm = 0, uint32_t free_bar = 0) {
     constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
     static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
     if constexpr (P > 0) {
@@ -518,14 +520,18 @@ template <int N> struct TeamFftX {
       tm_ld4(tm + 16u, b[0], b[2], b[1], b[3]);
       tm_ld4(tm + (16u << 16) + 16u, b[4], b[6], b[5], b[7]);
       tm_wait_ld();
-      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm);
+      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm, free_bar);
     } else if constexpr (P < NPASS - 1) {
       f2 wn[7];
       load_tw<P + 1>(wn, tw, tau);
       team_sync<WORKER>(bar);
       il_load<0>(A.ld, a, b);
       if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
-      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm);
+      if constexpr (TM && P == NPASS - 3) {
+        if (free_bar != 0u && (tau & 31) == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(free_bar) : "memory");
+      }
+      pass_il<P + 1, TM>(a, b, A, tw, tau, bar, wn, tm, free_bar);
     }
   }
   // the eight stores of a radix-8 pass / the eight loads after it, offsets as immediates
@@ -551,9 +557,10 @@ template <int N> struct TeamFftX {
   // tm: the warp's tensor-memory address (its 32 lanes, 32 columns); spectrum bins of lane l on return:
   // tm_tau(l) + TPR r
   static __device__ __forceinline__ void run2_tm(f2 (&a)[8], f2 (&b)[8], const Addr &A,
-                                                 const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
+                                                 const f2 *__restrict__ tw, int tau, int bar, uint32_t tm,
+                                                 uint32_t free_bar = 0) {
     const f2 w0[7] = {};
-    pass_il<0, true>(a, b, A, tw, tau, bar, w0, tm);
+    pass_il<0, true>(a, b, A, tw, tau, bar, w0, tm, free_bar);
   }
 };
 
@@ -607,17 +614,25 @@ struct TeamFft8x256 {
       load_t<r + 1>(ld, a, b);
     }
   }
-  // xT: the row's exchange buffer; A: make_addr_il(xT + (tau >> 5) REGION, tau & 31); tw: the tables above
-  static __device__ __forceinline__ void run2(f2 (&a)[8], f2 (&b)[8], uint32_t xT, const typename F256::Addr &A,
-                                              const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
+  // xT: the row's exchange buffer; A: make_addr_il(xT + (tau >> 5) REGION, tau & 31); tw: the tables above.
+  // front: the radix-8 pass; the caller then waits until the team has released the buffer (free_bar of
+  // the previous row), calls store, makes ONE team-wide barrier, and calls back -- which releases the
+  // buffer (free_bar) as soon as the warp has made its last read of its region.  Between back and the
+  // next store a warp runs free of the team.
+  static __device__ __forceinline__ void front(f2 (&a)[8], f2 (&b)[8]) {
     RadixP<8>::run(a);
     RadixP<8>::run(b);
+  }
+  static __device__ __forceinline__ void store(const f2 (&a)[8], const f2 (&b)[8], uint32_t xT, int tau) {
     store_t<0>(xT + 16u * (uint32_t)tau, a, b);
+  }
+  static __device__ __forceinline__ void back(f2 (&a)[8], f2 (&b)[8], uint32_t xT, const typename F256::Addr &A,
+                                              const f2 *__restrict__ tw, int tau, int bar, uint32_t tm,
+                                              uint32_t free_bar) {
     const int w = tau >> 5, lane = tau & 31;
     f2 t[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) t[r] = tw[w * 256 + lane + 32 * r];
-    team_sync<256>(bar);
     load_t<0>(xT + (uint32_t)w * REGION + 16u * (uint32_t)lane, a, b);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -625,7 +640,7 @@ struct TeamFft8x256 {
       b[r] = f2_cmul(b[r], t[r]);
     }
     __syncwarp();  // the warp has read its region; its own exchange may overwrite it
-    F256::run2_tm(a, b, A, tw + TW_A, lane, bar, tm);
+    F256::run2_tm(a, b, A, tw + TW_A, lane, bar, tm, free_bar);
   }
 };
 
