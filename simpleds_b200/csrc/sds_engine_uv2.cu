@@ -37,11 +37,15 @@ template <int N, int LEG> struct UvCfg {
   static constexpr int ROWB = 2 * VALB + 2 * N;       // set 0 | set 1 | flags 0 | flags 1
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = N * 8;
-  static constexpr int XREGION = NWORKER * ROWS * 2 * BUF;
+  // the two lockstep transforms exchange through one padded buffer of 16-byte slots (TeamFftX::run2_il);
+  // one-warp teams whose last pass has radix 4 (N = 256) make their last exchange through tensor memory
+  static constexpr bool TM = TeamFftX<N>::TM_OK;
+  static constexpr int XROW = TeamFftX<N>::IL_BYTES;
+  static constexpr int XREGION = NWORKER * ROWS * XROW;
   static constexpr int TW_BYTES = ((fft_tw_total(N) * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | UV_STAGES slots | 2 N floats (complex sums over times)
   static constexpr int WORKER_BYTES = 64 + UV_STAGES * SLOT + 8 * N;
-  static constexpr int SMEM = BUF + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
+  static constexpr int SMEM = 128 + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
 
 // acc + b conj(a)
@@ -59,20 +63,26 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t s0 = smem_u32(smem_raw);
-  unsigned char *smem = smem_raw + (((s0 + C::BUF - 1u) & ~(uint32_t)(C::BUF - 1)) - s0);
+  unsigned char *smem = smem_raw + (((s0 + 127u) & ~127u) - s0);
+  // shared-space addresses passed through an empty asm: not re-derived inside the step loop (sds_engine_f32.cu)
+  uint32_t sb_a = smem_u32(smem);
+  asm volatile("" : "+r"(sb_a));
 
-  f2 *tw_s = reinterpret_cast<f2 *>(smem + C::XREGION);
+  f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
     tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   const int lane_zero = (int)(threadIdx.x & 31u) * P.zero;  // see sds_engine_f32.cu (int_time load)
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;
-  const uint32_t xa = smem_u32(smem) + (uint32_t)((wid * ROWS + sub) * 2) * C::BUF;
-  const typename FFT::Addr fa = FFT::make_addr(xa, tau);
-  unsigned char *wbase = smem + C::XREGION + C::TW_BYTES + (size_t)wid * C::WORKER_BYTES;
+  uint32_t xa = sb_a + (uint32_t)(wid * ROWS + sub) * C::XROW;
+  uint32_t wb_a = sb_a + C::XREGION + C::TW_BYTES + (uint32_t)wid * C::WORKER_BYTES;
+  asm volatile("" : "+r"(xa));
+  asm volatile("" : "+r"(wb_a));
+  const typename FFT::Addr fa = FFT::make_addr_il(xa, tau);
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(__cvta_shared_to_generic(wb_a));
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + 64;
-  const uint32_t full_a = smem_u32(full), stages_a = smem_u32(stages);
+  const uint32_t full_a = wb_a, stages_a = wb_a + 64;
   // per-worker complex sums over times of (sum_i A2_i) conj(sum_j A1_j): (re, im) per delay
   f2 *pw_s = reinterpret_cast<f2 *>(stages + UV_STAGES * C::SLOT);
   for (int i = tl; i < N; i += TEAM) pw_s[i] = 0ull;
@@ -80,7 +90,17 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
     for (int i = 0; i < UV_STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __shared__ uint32_t tm_base_s;
+  if (C::TM && threadIdx.x < 32) tm_alloc<32>(smem_u32(&tm_base_s));
+  if (C::TM) tm_fence_before();
   __syncthreads();
+  uint32_t tm_a = 0;
+  if (C::TM) {
+    tm_fence_after();
+    tm_a = tm_base_s + (((threadIdx.x >> 5) & 3u) * 32u << 16);
+  }
+  // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
+  const int tau_out = C::TM ? FFT::tm_tau(tau) : tau;
 
   float tapdf[8];
 #pragma unroll
@@ -295,7 +315,8 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
           }
         }
       }
-      FFT::run2(va, vb, fa, tw_s, tau, bar_id);
+      if (C::TM) FFT::run2_tm(va, vb, fa, tw_s, tau, bar_id, tm_a);
+      else FFT::run2_il(va, vb, fa, tw_s, tau, bar_id);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         Sa[r] = f2_add(Sa[r], va[r]);
@@ -380,7 +401,7 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
     // flush the item: fp64 atomics on (re, im), fftshift as an index rotation
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int kshift = (tau + TPR * r + N / 2) % N;
+      const int kshift = (tau_out + TPR * r + N / 2) % N;
       f2 ca = Cauto[r];
 #pragma unroll
       for (int off = TPR; off < 32; off <<= 1) ca = f2_add(ca, f2_shfl_xor(ca, off));
@@ -407,6 +428,11 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
       }
     }
   }
+  if (C::TM) {
+    tm_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tm_dealloc<32>(tm_base_s);
+  }
 }
 
 template <int N, int LEG>
@@ -424,6 +450,8 @@ static int launch_uv2(const EngineParams &P, cudaStream_t st, int *launches) {
   SDS_CUDA(cudaGetDevice(&dev));
   SDS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   SDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, engine_uv2_kernel<N, LEG>, C::THREADS, C::SMEM));
+  // (the occupancy query answers 1 for a kernel that allocates tensor memory: sds_engine_f32.cu)
+  if (C::TM && per_sm < C::MINB) per_sm = C::MINB;
   if (per_sm < 1) {
     set_error("sds_engine_run: two-set kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
