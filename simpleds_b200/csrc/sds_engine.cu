@@ -20,6 +20,7 @@
 //   end of a time: P += |S1|^2 (the sum over ALL ordered pairs factorises),
 //   end of an item: fp64 atomics into the outputs (fftshift = index rotation).
 #include "sds_engine.cuh"
+#include "sds_packed.cuh"
 
 namespace sds {
 
@@ -80,6 +81,67 @@ __global__ void engine_setup_kernel(const int32_t *__restrict__ goff, int ngroup
   }
 }
 
+// ---- complex128 transform of length 256, last exchange through tensor memory ------------------------
+// The fp64 data leg is bound by the shared-memory data pipe (89 % busy: 16-byte values through two
+// exchanges and 13 twiddle loads per row).  Its last exchange goes through tensor memory exactly like the
+// packed fp32 engine's (sds_packed.cuh, TeamFftX::pass_il): a double is a 64-bit column pair, which the
+// 16x256b fragment keeps whole, so the real parts of the thread's eight values travel in columns [0, 16)
+// and the imaginary parts in [16, 32) -- the two planes play the role of the fp32 engine's data and noise
+// rows.  Afterwards lane l acts as team member tm_tau(l) and owns bins tm_tau(l) + 32 r.
+struct TeamFftD256 {
+  using F = TeamFftX<256>;
+  static __device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+  static __device__ __forceinline__ double dbl(unsigned long long v) { return __longlong_as_double((long long)v); }
+  static __device__ __forceinline__ void run_tm(cpx<double> (&v)[8], cpx<double> *buf, const cpx<double> *__restrict__ tw,
+                                                int tau, uint32_t tm) {
+    constexpr int TPR = 32;
+    {  // pass 0: radix 8, Stockham store (NS = 1), as TeamFft<double, 256>::pass<0>
+      cpx<double> a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = v[q];
+      Radix<double, 8>::run(a);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) buf[fft_pad(tau * 8 + p)] = a[brev(p, 3)];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = buf[fft_pad(tau + TPR * r)];
+    }
+    {  // pass 1: twiddles, radix 8, tensor-memory exchange
+      constexpr int OFF = fft_tw_offset(256, 1);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], tw[OFF + (q - 1) * TPR + tau]);
+      Radix<double, 8>::run(v);
+      tm_st8(tm, bits(v[brev(0, 3)].x), bits(v[brev(1, 3)].x), bits(v[brev(2, 3)].x), bits(v[brev(3, 3)].x),
+             bits(v[brev(4, 3)].x), bits(v[brev(5, 3)].x), bits(v[brev(6, 3)].x), bits(v[brev(7, 3)].x));
+      tm_st8(tm + 16u, bits(v[brev(0, 3)].y), bits(v[brev(1, 3)].y), bits(v[brev(2, 3)].y), bits(v[brev(3, 3)].y),
+             bits(v[brev(4, 3)].y), bits(v[brev(5, 3)].y), bits(v[brev(6, 3)].y), bits(v[brev(7, 3)].y));
+    }
+    const int tl = F::tm_tau(tau);  // the team member this lane acts as from here on
+    constexpr int OFF2 = fft_tw_offset(256, 2);
+    tm_wait_st();
+    unsigned long long re[8], im[8];
+    // loaded slot (tau4 t2 tau3) is logical slot (tau4 tau3 t2): 1 <-> 2, 5 <-> 6
+    tm_ld4(tm, re[0], re[2], re[1], re[3]);
+    tm_ld4(tm + (16u << 16), re[4], re[6], re[5], re[7]);
+    tm_ld4(tm + 16u, im[0], im[2], im[1], im[3]);
+    tm_ld4(tm + (16u << 16) + 16u, im[4], im[6], im[5], im[7]);
+    tm_wait_ld();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = {dbl(re[r]), dbl(im[r])};
+    // pass 2: radix 4, two butterflies (m = 0, 1) on slots m + 2 q
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      cpx<double> a[4];
+      a[0] = v[m];
+#pragma unroll
+      for (int q = 1; q < 4; ++q) a[q] = cmul(v[m + 2 * q], tw[OFF2 + (m * 3 + (q - 1)) * TPR + tl]);
+      Radix<double, 4>::run(a);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[m + 2 * p] = a[brev(p, 2)];
+    }
+  }
+};
+
 // ---- the fused kernel ---------------------------------------------------------
 template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr int TPR = N / 8;
@@ -101,14 +163,22 @@ template <typename T, int N, int LEGS> struct EngCfg {
   // per worker: barriers (64 B) | STAGES slots | 2 exchange buffers per row |
   // thermal leg: 6 values per thread (first-channel sums of its two runs, for the left neighbour)
   static constexpr int NB_BYTES = (LEGS & LEG_THERMAL) ? 6 * WORKER * (int)sizeof(T) : 0;
-  // the thermal leg transforms nothing: no exchange buffers, and a register budget for 16 warps / SM
-  static constexpr int XB_BYTES = (LEGS & (LEG_DATA | LEG_NOISE)) ? 2 * ROWS * BUF : 0;
   // the fp64 data leg: a 2-slot ring leaves shared memory for three CTAs (12 warps) per SM at
   // N = 256, which beats the deeper prefetch at 8 warps (measured 7.23 -> 6.69 ms per HERA-350 batch)
   static constexpr bool D64 = sizeof(T) == 8 && LEGS == LEG_DATA;
+  static constexpr bool TM = D64 && N == 256;  // last exchange through tensor memory (TeamFftD256)
+#ifndef ENG_D64_TACC
+#define ENG_D64_TACC 1
+#endif
+  // the fp64 accumulators (S1: 32 words, S2: 16, the per-time sums: 16) in thread-private tensor-memory
+  // columns [32, 96), as in the fp32 engine: 128 registers, four CTAs per SM
+  static constexpr bool TACC = TM && ENG_D64_TACC;
+  static constexpr int TM_COLS = TACC ? 128 : 32;
+  // the thermal leg transforms nothing: no exchange buffers, and a register budget for 16 warps / SM
+  static constexpr int XB_BYTES = (LEGS & (LEG_DATA | LEG_NOISE)) ? (TM ? 1 : 2) * ROWS * BUF : 0;
   static constexpr int STAGES = D64 ? 2 : ENG_STAGES;
   static constexpr int MINB = (LEGS == LEG_THERMAL) ? (512 / THREADS < 1 ? 1 : 512 / THREADS)
-                              : D64 ? (384 / THREADS < 1 ? 1 : 384 / THREADS) : ENG_MINBLOCKS;
+                              : TACC ? 4 : D64 ? (384 / THREADS < 1 ? 1 : 384 / THREADS) : ENG_MINBLOCKS;
   static constexpr int WORKER_BYTES = 64 + STAGES * SLOT + XB_BYTES + NB_BYTES;
   static constexpr int SMEM = TAB_BYTES + NWORKER * WORKER_BYTES;
 };
@@ -143,7 +213,22 @@ engine_kernel(const __grid_constant__ EngineParams P) {
     for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __shared__ uint32_t tm_base_s;
+  if (C::TM && threadIdx.x < 32) tm_alloc<C::TM_COLS>(smem_u32(&tm_base_s));
+  if (C::TM) tm_fence_before();
   __syncthreads();
+  uint32_t tm_a = 0;
+  if (C::TM) {
+    tm_fence_after();
+    tm_a = tm_base_s + ((((uint32_t)threadIdx.x >> 5) & 3u) * 32u << 16);
+  }
+  // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
+  const int tau_out = C::TM ? TeamFftX<256>::tm_tau(tau & 31) : tau;
+  constexpr uint32_t TC_S1 = 32, TC_S2 = 64, TC_PW = 80;
+  if (C::TACC) {
+    const uint32_t z16[16] = {};
+    tm_st_w16(tm_a + TC_PW, z16);
+  }
 
   // per-thread constants: taper * delta_f at this thread's 8 transform channels
   T tapdf[8];
@@ -248,6 +333,13 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       tA[r] = tB[r] = tC[r] = (T)0;
     }
 
+    if constexpr (C::TACC) {
+      const uint32_t z32[32] = {};
+      const uint32_t z16[16] = {};
+      tm_st_w32(tm_a + TC_S1, z32);
+      tm_st_w16(tm_a + TC_S2, z16);
+      tm_wait_st();
+    }
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
     int64_t it_off = (int64_t)b0 * P.ntime + t0;            // int_time index of row 0
@@ -286,11 +378,51 @@ engine_kernel(const __grid_constant__ EngineParams P) {
           const T m = (keep >> r) & 1u ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
           v[r] = {(T)c.x * m, (T)c.y * m};
         }
-        TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
+        if constexpr (C::TM) TeamFftD256::run_tm(v, bufA, tw_s, tau, tm_a);
+        else TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
+        if constexpr (C::TACC) {  // (the exchange inside the transform fenced the stores of the previous row)
+          uint32_t w32[32], w16[16];
+          tm_ld_w32(tm_a + TC_S1, w32);
+          tm_ld_w16(tm_a + TC_S2, w16);
+          tm_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            S1[r] = {(T)TeamFftD256::dbl(f2_from_words(w32[4 * r], w32[4 * r + 1])),
+                     (T)TeamFftD256::dbl(f2_from_words(w32[4 * r + 2], w32[4 * r + 3]))};
+            S2[r] = (T)TeamFftD256::dbl(f2_from_words(w16[2 * r], w16[2 * r + 1]));
+          }
+        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           S1[r] = cadd(S1[r], v[r]);
           S2[r] += v[r].x * v[r].x + v[r].y * v[r].y;
+        }
+        if constexpr (C::TACC) {
+          if (ci0 + ROWS >= ng) {  // the time closes with this row
+            uint32_t pw[16];
+            tm_ld_w16(tm_a + TC_PW, pw);
+            tm_wait_ld();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const double pv = TeamFftD256::dbl(f2_from_words(pw[2 * r], pw[2 * r + 1])) +
+                                (double)(S1[r].x * S1[r].x + S1[r].y * S1[r].y);
+              const unsigned long long b = TeamFftD256::bits(pv);
+              pw[2 * r] = (uint32_t)b; pw[2 * r + 1] = (uint32_t)(b >> 32);
+              S1[r] = {(T)0, (T)0};
+            }
+            tm_st_w16(tm_a + TC_PW, pw);
+          }
+          uint32_t w32[32], w16[16];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const unsigned long long bx = TeamFftD256::bits((double)S1[r].x), by = TeamFftD256::bits((double)S1[r].y),
+                                     b2 = TeamFftD256::bits((double)S2[r]);
+            w32[4 * r] = (uint32_t)bx; w32[4 * r + 1] = (uint32_t)(bx >> 32);
+            w32[4 * r + 2] = (uint32_t)by; w32[4 * r + 3] = (uint32_t)(by >> 32);
+            w16[2 * r] = (uint32_t)b2; w16[2 * r + 1] = (uint32_t)(b2 >> 32);
+          }
+          tm_st_w32(tm_a + TC_S1, w32);
+          tm_st_w16(tm_a + TC_S2, w16);
         }
       }
 
@@ -378,7 +510,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         ++ct;
         ++it_off;
         ++rid_t;
-        if (HAS_D) {
+        if (HAS_D && !C::TACC) {
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             cpx<T> sfull = S1[r];
@@ -455,9 +587,23 @@ engine_kernel(const __grid_constant__ EngineParams P) {
 
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
     const int64_t obase = (((int64_t)gout * P.nspw + s) * P.npol + p) * N;
+    if constexpr (C::TACC) {
+      uint32_t w16[16], pw[16];
+      tm_wait_st();
+      tm_ld_w16(tm_a + TC_S2, w16);
+      tm_ld_w16(tm_a + TC_PW, pw);
+      tm_wait_ld();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        S2[r] = (T)TeamFftD256::dbl(f2_from_words(w16[2 * r], w16[2 * r + 1]));
+        Pw[r] = (T)TeamFftD256::dbl(f2_from_words(pw[2 * r], pw[2 * r + 1]));
+      }
+      const uint32_t z16[16] = {};
+      tm_st_w16(tm_a + TC_PW, z16);
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int kshift = (tau + TPR * r + N / 2) % N;
+      const int kshift = (tau_out + TPR * r + N / 2) % N;
       if (HAS_D) {
         T s2 = S2[r];
 #pragma unroll
@@ -490,6 +636,11 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         atomicAdd(P.th_auto + o, f * th_auto_acc);
       }
     }
+  }
+  if (C::TM) {
+    tm_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tm_dealloc<C::TM_COLS>(tm_base_s);
   }
 }
 
@@ -538,6 +689,8 @@ static int launch_engine(const EngineParams &P, cudaStream_t st) {
     set_error("sds_engine_run: kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
   }
+  // (the occupancy query answers 1 for a kernel that allocates tensor memory: sds_engine_f32.cu)
+  if (C::TM && per_sm < C::MINB) per_sm = C::MINB;
   engine_kernel<T, N, LEGS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
   SDS_LAUNCH_CHECK("engine_kernel");
   ++g_last_launches;

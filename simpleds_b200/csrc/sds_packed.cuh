@@ -367,9 +367,12 @@ template <int N> struct TeamFftX {
 #pragma unroll
       for (int q = 1; q < R; ++q) w[m * (R - 1) + (q - 1)] = tw[OFF + (m * (R - 1) + (q - 1)) * TPR + tt];
   }
-  template <int P, bool TWO>
+  // TM1 (one transform only): the LAST exchange through tensor memory, as in pass_il below (16 columns)
+  template <int P, bool TWO, bool TM1 = false>
   static __device__ __forceinline__ void pass(f2 (&a)[8], f2 (&b)[8], const Addr &A,
-                                              const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7]) {
+                                              const f2 *__restrict__ tw, int tau, int bar, const f2 (&wp)[7],
+                                              uint32_t tm = 0) {
+    static_assert(!(TM1 && TWO), "the pair goes through pass_il");
     constexpr int R = fft_radix(N, P), NB = 8 / R, NS = fft_ns(N, P), LG = ilog2(R);
     static_assert(P == NPASS - 1 || (R == 8 && NB == 1), "storing passes have radix 8");
     if constexpr (P > 0) {
@@ -392,7 +395,10 @@ template <int N> struct TeamFftX {
       }
       RadixP<R>::run(x);
       if (TWO) RadixP<R>::run(y);
-      if constexpr (P < NPASS - 1) {
+      if constexpr (TM1 && P == NPASS - 2) {
+        tm_st8(tm, x[brev(0, 3)], x[brev(1, 3)], x[brev(2, 3)], x[brev(3, 3)], x[brev(4, 3)], x[brev(5, 3)],
+               x[brev(6, 3)], x[brev(7, 3)]);
+      } else if constexpr (P < NPASS - 1) {
 #pragma unroll
         for (int p = 0; p < R; ++p) {
           const uint32_t ad = A.st[P] ^ (8u * (uint32_t)fft_pad(p * NS));
@@ -407,7 +413,15 @@ template <int N> struct TeamFftX {
         }
       }
     }
-    if constexpr (P < NPASS - 1) {
+    if constexpr (TM1 && P == NPASS - 2) {
+      f2 wn[7];
+      load_tw<P + 1>(wn, tw, tm_tau(tau));
+      tm_wait_st();
+      tm_ld4(tm, a[0], a[2], a[1], a[3]);  // (slot renaming: see pass_il)
+      tm_ld4(tm + (16u << 16), a[4], a[6], a[5], a[7]);
+      tm_wait_ld();
+      pass<P + 1, TWO, TM1>(a, b, A, tw, tau, bar, wn, tm);
+    } else if constexpr (P < NPASS - 1) {
       f2 wn[7];
       load_tw<P + 1>(wn, tw, tau);
       team_sync<WORKER>(bar);
@@ -418,7 +432,7 @@ template <int N> struct TeamFftX {
         if (TWO) b[r] = lds_f2_off<BUFB>(ad);
       }
       if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);  // reads done before the next pass writes
-      pass<P + 1, TWO>(a, b, A, tw, tau, bar, wn);
+      pass<P + 1, TWO, TM1>(a, b, A, tw, tau, bar, wn, tm);
     }
   }
   // NOTE: the caller must team-sync between two calls on the same buffers (the engine's step
@@ -432,6 +446,12 @@ template <int N> struct TeamFftX {
                                              int tau, int bar) {
     const f2 w0[7] = {};
     pass<0, false>(a, a, A, tw, tau, bar, w0);
+  }
+  // one transform, last exchange through tensor memory (TM_OK lengths); bins of lane l on return: tm_tau(l) + TPR r
+  static __device__ __forceinline__ void run_tm1(f2 (&a)[8], const Addr &A, const f2 *__restrict__ tw,
+                                                 int tau, int bar, uint32_t tm) {
+    const f2 w0[7] = {};
+    pass<0, false, true>(a, a, A, tw, tau, bar, w0, tm);
   }
 
   // ---- interleaved pair: the two lockstep transforms share ONE buffer of 16-byte slots -------
