@@ -35,6 +35,9 @@ namespace sds {
 #ifndef E3_TACC10
 #define E3_TACC10 0  // tensor-memory accumulators for the noise + fp64-thermal leg: measured SLOWER (7.44 vs 5.96 ms:
 #endif               // 80 words of read-modify-write per row and 76 B of spills at 128 registers); kept for the record
+#ifndef E3_F4_SPLIT
+#define E3_F4_SPLIT 1  // four-step: arrive / wait instead of a blocking team barrier
+#endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
 #endif
@@ -151,13 +154,19 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t full_a = wb_a, stages_a = wb_a + C::HEAD;  // shared-space addresses
   const uint32_t free_a = wb_a + 32;  // four-step: the buffer-release barrier
   uint32_t par_f = 1u;                // its phase parity (a fresh barrier passes a wait on parity 1)
+  const uint32_t stored_a = wb_a + 40, flag_a = wb_a + 48;
+  uint32_t par_s = 0u, seq_f4 = 0u;
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
   float *pw_s = reinterpret_cast<float *>(stages + C::STAGES * C::SLOT);
   if (!C::TACC && !C::TACC10)
     for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1);
-    if (C::F4) mbar_init(&full[4], TEAM / 32);  // four-step: "the team's exchange buffer is free" (one arrival per warp)
+    if (C::F4) {
+      mbar_init(&full[4], TEAM / 32);  // four-step: "the team's exchange buffer is free" (one arrival per warp)
+      mbar_init(&full[5], TEAM / 32);  // four-step: "the row's transposed stores are done"
+      full[6] = 0;                     // the two flag words of the invalid-sample vote
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // tensor memory for the last exchange: 32 columns per CTA, each warp its own 32 lanes
@@ -461,7 +470,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
         }
       }
-      if (HAS_T) {  // thermal sums first: nsample^-1/2 is dead before the transforms start
+      // thermal sums ahead of the transforms: nsample^-1/2 is dead before the butterflies start (four-step:
+      // in the shadow of the team-wide exchange, between a warp's arrival and its wait)
+      auto thermal_sums = [&]() {
         const f2 it2 = f2_make(itv, itv);
         if constexpr (C::TACC) {
           // (the stores of the previous row were fenced by its exchange)
@@ -495,7 +506,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           tm_st_w16(tm_a + TC_T, w16);
           tm_st_w8(tm_a + TC_T + 16, w8);
         }
-      }
+      };
+      if (HAS_T && !(C::F4 && E3_F4_SPLIT)) thermal_sums();
       // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
       // with any invalid sample books what the full sums above contain but the panel must not
       auto book_deficits = [&]() {
@@ -526,8 +538,28 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           mbar_wait_a(free_a, par_f);  // every warp has made its last read of the previous row's buffer
           par_f ^= 1u;
           TeamFft8x256::store(vd, vn, xa, tau);
+#if E3_F4_SPLIT
+          // the row's ONE team-wide synchronisation as an arrive / wait pair on an mbarrier (one arrival
+          // per warp), with the thermal sums in between; the "some sample of the row is invalid" vote
+          // travels as the row's sequence number in one of two flag words (a word is rewritten two rows
+          // later, when every warp has long read it)
+          ++seq_f4;
+          {
+            const bool wd = __any_sync(0xffffffffu, active && !all_ok);
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) {
+              if (wd) sts_u32(flag_a + 4u * (seq_f4 & 1u), seq_f4);
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(stored_a) : "memory");
+            }
+          }
+          if (HAS_T) thermal_sums();
+          mbar_wait_a(stored_a, par_s);
+          par_s ^= 1u;
+          dirty_row = lds_u32(flag_a + 4u * (seq_f4 & 1u)) == seq_f4;
+#else
           // the row's ONE team-wide barrier, carrying the "some sample of the row is invalid" vote
           dirty_row = team_any<TEAM>(active && !all_ok, bar_id);
+#endif
           if (HAS_T && dirty_row) {  // rare: the booking re-reads nsample of the staged row
             book_deficits();
             team_sync<TEAM>(bar_id);
