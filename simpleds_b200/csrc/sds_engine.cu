@@ -116,7 +116,7 @@ struct TeamFftD256 {
       tm_st8(tm + 16u, bits(v[brev(0, 3)].y), bits(v[brev(1, 3)].y), bits(v[brev(2, 3)].y), bits(v[brev(3, 3)].y),
              bits(v[brev(4, 3)].y), bits(v[brev(5, 3)].y), bits(v[brev(6, 3)].y), bits(v[brev(7, 3)].y));
     }
-    const int tl = F::tm_tau(tau);  // the team member this lane acts as from here on
+    // (this lane acts as team member tm_tau(tau) from here on; the last pass's twiddles are stored permuted)
     constexpr int OFF2 = fft_tw_offset(256, 2);
     tm_wait_st();
     unsigned long long re[8], im[8];
@@ -134,7 +134,7 @@ struct TeamFftD256 {
       cpx<double> a[4];
       a[0] = v[m];
 #pragma unroll
-      for (int q = 1; q < 4; ++q) a[q] = cmul(v[m + 2 * q], tw[OFF2 + (m * 3 + (q - 1)) * TPR + tl]);
+      for (int q = 1; q < 4; ++q) a[q] = cmul(v[m + 2 * q], tw[OFF2 + (m * 3 + (q - 1)) * TPR + tau]);
       Radix<double, 4>::run(a);
 #pragma unroll
       for (int p = 0; p < 4; ++p) v[m + 2 * p] = a[brev(p, 2)];
@@ -198,7 +198,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   cpx<float> *twf_s = SAME ? reinterpret_cast<cpx<float> *>(smem)
                            : reinterpret_cast<cpx<float> *>(smem + C::TW_BYTES);
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS) {
-    if (C::TW_BYTES) tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[i];
+    if (C::TW_BYTES) tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[C::TM ? TeamFftX<N>::tm_tw_src(i) : i];
     if (C::TWF_BYTES) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
   }
   const int wid = threadIdx.x / WORKER, wl = threadIdx.x % WORKER;

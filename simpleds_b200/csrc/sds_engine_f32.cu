@@ -134,7 +134,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     TeamFft8x256::fill_tables(tw_s, threadIdx.x, C::THREADS);
   } else {
     for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
-      tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
+      tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[(C::TM || C::TM1) ? FFT::tm_tw_src(i) : i];
   }
   // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
   uint32_t xa = sb_a + (uint32_t)(wid * ROWS + sub) * C::XROW;

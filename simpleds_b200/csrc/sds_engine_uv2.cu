@@ -70,7 +70,7 @@ engine_uv2_kernel(const __grid_constant__ EngineParams P) {
 
   f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
   for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
-    tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[i];
+    tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[C::TM ? FFT::tm_tw_src(i) : i];
   const int wid = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   const int lane_zero = (int)(threadIdx.x & 31u) * P.zero;  // see sds_engine_f32.cu (int_time load)
   const int sub = tl / TPR, tau = tl % TPR, bar_id = 1 + wid;

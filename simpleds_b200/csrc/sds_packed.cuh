@@ -415,7 +415,7 @@ template <int N> struct TeamFftX {
     }
     if constexpr (TM1 && P == NPASS - 2) {
       f2 wn[7];
-      load_tw<P + 1>(wn, tw, tm_tau(tau));
+      load_tw<P + 1>(wn, tw, tau);  // (the last pass's section is stored permuted: tm_tw_src)
       tm_wait_st();
       tm_ld4(tm, a[0], a[2], a[1], a[3]);  // (slot renaming: see pass_il)
       tm_ld4(tm + (16u << 16), a[4], a[6], a[5], a[7]);
@@ -484,6 +484,17 @@ template <int N> struct TeamFftX {
   // of the spectrum: bins tm_tau(l) + TPR r) and the loaded slots are renamed (low two bits swapped).
   static constexpr bool TM_OK = NPASS >= 2 && fft_radix(N, NPASS - 1) == 4 && TPR == 32;
   static __device__ __forceinline__ int tm_tau(int lane) { return ((lane & 3) << 3) | (lane >> 2); }
+  // The last pass looks its twiddles up as team member tm_tau(lane): read through that index the lanes of
+  // a warp would hit shared-memory banks 2 ways (8-byte entries; 4 ways for 16-byte complex128 entries),
+  // so kernels that use the tensor-memory exchange keep the LAST pass's section of the table permuted --
+  // entry [k][lane] holds the twiddle of member tm_tau(lane) -- and every lane reads its own column.
+  // Table index i of the shared copy <- index tm_tw_src(i) of the plan's table.
+  static __host__ __device__ constexpr int tm_tw_src(int i) {
+    constexpr int OFFL = fft_tw_offset(N, NPASS - 1);
+    if (i < OFFL) return i;
+    const int k = (i - OFFL) / TPR, lane = (i - OFFL) % TPR;
+    return OFFL + k * TPR + (((lane & 3) << 3) | (lane >> 2));
+  }
   // free_bar (TM only): an mbarrier on which lane 0 arrives once the warp has made its last read of the
   // exchange region (the four-step schedule lets the team overwrite the region as soon as all warps have)
   template <int P, bool TM = false>
@@ -530,7 +541,7 @@ template <int N> struct TeamFftX {
     }
     if constexpr (TM && P == NPASS - 2) {
       f2 wn[7];
-      load_tw<P + 1>(wn, tw, tm_tau(tau));
+      load_tw<P + 1>(wn, tw, tau);  // (the last pass's section is stored permuted: tm_tw_src)
 #ifndef SDS_TM_NOWAIT
       tm_wait_st();
 #endif
@@ -612,7 +623,9 @@ struct TeamFft8x256 {
     for (int p = 1; p < NP; ++p) {
       const int R = fft_radix(256, p), NB = 8 / R, NS = fft_ns(256, p), off = fft_tw_offset(256, p);
       for (int i = tid; i < NB * (R - 1) * 32; i += nthreads) {
-        const int tau = i & 31, mq = i >> 5, m = mq / (R - 1), q = mq % (R - 1) + 1;
+        // (last pass: the column of lane l holds the twiddle of team member tm_tau(l), see tm_tw_src)
+        const int tau = p == NP - 1 ? F256::tm_tau(i & 31) : (i & 31);
+        const int mq = i >> 5, m = mq / (R - 1), q = mq % (R - 1) + 1;
         const int k = (tau + 32 * m) % NS;
         float sn, cs;
         sincospif(-2.0f * (float)(q * k) / (float)(NS * R), &sn, &cs);
