@@ -92,19 +92,34 @@ struct TeamFftD256 {
   using F = TeamFftX<256>;
   static __device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
   static __device__ __forceinline__ double dbl(unsigned long long v) { return __longlong_as_double((long long)v); }
-  static __device__ __forceinline__ void run_tm(cpx<double> (&v)[8], cpx<double> *buf, const cpx<double> *__restrict__ tw,
+  // first exchange: a complex128 value is one 16-byte slot of the padded layout of the fp32 engine's
+  // interleaved exchange (slot j at j + (j >> 3): conflict-free 128-bit accesses at [register + immediate])
+  template <int p> static __device__ __forceinline__ void store0(uint32_t st, const cpx<double> (&a)[8]) {
+    if constexpr (p < 8) {
+      sts_f2x2_off<16 * p>(st, bits(a[brev(p, 3)].x), bits(a[brev(p, 3)].y));
+      store0<p + 1>(st, a);
+    }
+  }
+  template <int r> static __device__ __forceinline__ void load0(uint32_t ld, cpx<double> (&v)[8]) {
+    if constexpr (r < 8) {
+      unsigned long long re, im;
+      lds_f2x2_off<16 * F::il_pad(32 * r)>(ld, re, im);
+      v[r] = {dbl(re), dbl(im)};
+      load0<r + 1>(ld, v);
+    }
+  }
+  // xa: shared-space address of the row's F::IL_BYTES exchange region
+  static __device__ __forceinline__ void run_tm(cpx<double> (&v)[8], uint32_t xa, const cpx<double> *__restrict__ tw,
                                                 int tau, uint32_t tm) {
     constexpr int TPR = 32;
-    {  // pass 0: radix 8, Stockham store (NS = 1), as TeamFft<double, 256>::pass<0>
+    {  // pass 0: radix 8, Stockham store (NS = 1)
       cpx<double> a[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) a[q] = v[q];
       Radix<double, 8>::run(a);
-#pragma unroll
-      for (int p = 0; p < 8; ++p) buf[fft_pad(tau * 8 + p)] = a[brev(p, 3)];
+      store0<0>(xa + 16u * (uint32_t)F::il_pad(8 * tau), a);
       __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = buf[fft_pad(tau + TPR * r)];
+      load0<0>(xa + 16u * (uint32_t)F::il_pad(tau), v);
     }
     {  // pass 1: twiddles, radix 8, tensor-memory exchange
       constexpr int OFF = fft_tw_offset(256, 1);
@@ -175,7 +190,7 @@ template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr bool TACC = TM && ENG_D64_TACC;
   static constexpr int TM_COLS = TACC ? 128 : 32;
   // the thermal leg transforms nothing: no exchange buffers, and a register budget for 16 warps / SM
-  static constexpr int XB_BYTES = (LEGS & (LEG_DATA | LEG_NOISE)) ? (TM ? 1 : 2) * ROWS * BUF : 0;
+  static constexpr int XB_BYTES = TM ? ROWS * TeamFftX<256>::IL_BYTES : (LEGS & (LEG_DATA | LEG_NOISE)) ? 2 * ROWS * BUF : 0;
   static constexpr int STAGES = D64 ? 2 : ENG_STAGES;
   static constexpr int MINB = (LEGS == LEG_THERMAL) ? (512 / THREADS < 1 ? 1 : 512 / THREADS)
                               : TACC ? 4 : D64 ? (384 / THREADS < 1 ? 1 : 384 / THREADS) : ENG_MINBLOCKS;
@@ -224,6 +239,8 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
   const int tau_out = C::TM ? TeamFftX<256>::tm_tau(tau & 31) : tau;
+  uint32_t xa_tm = smem_u32(stages + C::STAGES * C::SLOT);  // TM: one exchange region per worker (ROWS = 1)
+  asm volatile("" : "+r"(xa_tm));
   constexpr uint32_t TC_S1 = 32, TC_S2 = 64, TC_PW = 80;
   if (C::TACC) {
     const uint32_t z16[16] = {};
@@ -378,7 +395,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
           const T m = (keep >> r) & 1u ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
           v[r] = {(T)c.x * m, (T)c.y * m};
         }
-        if constexpr (C::TM) TeamFftD256::run_tm(v, bufA, tw_s, tau, tm_a);
+        if constexpr (C::TM) TeamFftD256::run_tm(v, xa_tm, tw_s, tau, tm_a);
         else TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
         if constexpr (C::TACC) {  // (the exchange inside the transform fenced the stores of the previous row)
           uint32_t w32[32], w16[16];
