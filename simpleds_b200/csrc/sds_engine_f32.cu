@@ -32,9 +32,6 @@ namespace sds {
 #ifndef E3_F4
 #define E3_F4 1  // N = 2048: one team-wide exchange, then one 256-point transform per warp (TeamFft8x256)
 #endif
-#ifndef E3_TACC10
-#define E3_TACC10 0  // tensor-memory accumulators for the noise + fp64-thermal leg: measured SLOWER (7.44 vs 5.96 ms:
-#endif               // 80 words of read-modify-write per row and 76 B of spills at 128 registers); kept for the record
 #ifndef E3_F4_SPLIT
 #define E3_F4_SPLIT 1  // four-step: arrive / wait instead of a blocking team barrier
 #endif
@@ -65,16 +62,16 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
   static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && LEGS == (LEG_DATA | LEG_NOISE | LEG_THERMAL) && !GAUSS &&
                                (N == 256 || (E3_F4 && N == 2048));
-  // TACC10: the same for the noise + fp64-thermal leg of the complex128 mode (one transform whose last
-  // exchange goes through tensor memory; 48 words of fp64 thermal sums, Sn1, Sn2, the per-time sums)
+  // TM1: the noise + fp64-thermal leg of the complex128 mode (one transform) makes its last exchange
+  // through tensor memory as well; its accumulators stay in registers (in tensor memory they measured
+  // slower: 7.44 vs 5.96 ms, 80 words of read-modify-write per row and spills at 128 registers)
   static constexpr bool TM1 = E3_TM && E3_TACC && LEGS == (LEG_NOISE | LEG_THERMAL64) && !GAUSS && TeamFftX<N>::TM_OK;
-  static constexpr bool TACC10 = TM1 && E3_TACC10;
-  static constexpr int STAGES = (TACC || TACC10) ? 2 : E3_STAGES;
+  static constexpr int STAGES = TACC ? 2 : E3_STAGES;
   // tensor-memory columns of one warp (exchange 32 + accumulators 88), and of the CTA: warps w and w + 4
   // share TMEM lanes, so every set of four warps has its own column range
-  static constexpr int TM_WCOLS = (TACC || TACC10) ? 128 : 32;
+  static constexpr int TM_WCOLS = TACC ? 128 : 32;
   static constexpr int TM_COLS = TM_WCOLS * (THREADS / 128);
-  static constexpr int WARPS_PER_SM = (TACC || TACC10 || (NOISE_ONLY && THREADS <= 128)) ? 16 : E3_WARPS_PER_SM;
+  static constexpr int WARPS_PER_SM = (TACC || (NOISE_ONLY && THREADS <= 128)) ? 16 : E3_WARPS_PER_SM;
   static constexpr int MINB = (WARPS_PER_SM * 32) / THREADS < 1 ? 1 : (WARPS_PER_SM * 32) / THREADS;
   static constexpr int VISB = (LEGS & LEG_DATA) ? 8 * N : 0;
   static constexpr int ROWB = VISB + 5 * N;             // vis 8N (data leg only) | nsample 4N | flags N
@@ -94,7 +91,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   static constexpr int TW_BYTES = ((TW_ENTRIES * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
   static constexpr int HEAD = 192;
-  static constexpr int WORKER_BYTES = HEAD + STAGES * SLOT + ((TACC || TACC10) ? 0 : 8 * N);
+  static constexpr int WORKER_BYTES = HEAD + STAGES * SLOT + (TACC ? 0 : 8 * N);
   // XALIGN bytes of slack in front: the exchange region is aligned at run time
   static constexpr int SMEM = XALIGN + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
 };
@@ -158,7 +155,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   uint32_t par_s = 0u, seq_f4 = 0u;
   // per-worker sums over times of |S1|^2: [0, N) data, [N, 2N) noise (touched once per time)
   float *pw_s = reinterpret_cast<float *>(stages + C::STAGES * C::SLOT);
-  if (!C::TACC && !C::TACC10)
+  if (!C::TACC)
     for (int i = tl; i < 2 * N; i += TEAM) pw_s[i] = 0.f;
   if (tl == 0) {
     for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1);
@@ -187,13 +184,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   if (C::TACC) {
     const uint32_t z16[16] = {};
     tm_st_w16(tm_a + TC_PW, z16);
-  }
-  // noise + fp64-thermal leg (TACC10): [0, 16) exchange | [16, 32) Sn1 | [32, 40) Sn2 | [40, 48) per-time
-  // |Sn1|^2 sums | [64, 96) dA, dB | [96, 112) dC
-  constexpr uint32_t T10_S1 = 16, T10_S2 = 32, T10_PW = 40, T10_AB = 64, T10_C = 96;
-  if (C::TACC10) {
-    const uint32_t z8[8] = {};
-    tm_st_w8(tm_a + T10_PW, z8);
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
   const int tau_out = C::F4 ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31) : (C::TM || C::TM1) ? FFT::tm_tau(tau) : tau;
@@ -318,16 +308,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       tm_st_w8(tm_a + TC_T + 16, z8);
       tm_wait_st();
     }
-    if constexpr (C::TACC10) {
-      const uint32_t z32[32] = {};
-      const uint32_t z16[16] = {};
-      const uint32_t z8[8] = {};
-      tm_st_w16(tm_a + T10_S1, z16);
-      tm_st_w8(tm_a + T10_S2, z8);
-      tm_st_w32(tm_a + T10_AB, z32);
-      tm_st_w16(tm_a + T10_C, z16);
-      tm_wait_st();
-    }
 
     // ---- consumer state ------------------------------------------------------------
     int ci0 = 0, ct = t0;                                   // first row / time of this step
@@ -376,9 +356,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     for (int step = 0; step < nsteps; ++step) {
       if (!C::F4) {
         team_sync<TEAM>(bar_id);  // everyone is done with the slot about to be refilled
-#ifndef E3_ISSUE_LATE
         if (pleft > 0) issue();
-#endif
       }
       const int i = ci0 + sub;
       const bool active = ROWS == 1 || i < ng;
@@ -572,18 +550,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
         else if (C::TM1) FFT::run_tm1(vn, fa, tw_s, tau, bar_id, tm_a);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
-        if constexpr (C::TACC10) {
-          // (the exchange inside the transform fenced the stores of the previous row)
-          uint32_t w16[16], w8[8];
-          tm_ld_w16(tm_a + T10_S1, w16);
-          tm_ld_w8(tm_a + T10_S2, w8);
-          tm_wait_ld();
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            Sn1[r] = f2_from_words(w16[2 * r], w16[2 * r + 1]);
-            Sn2[r] = __uint_as_float(w8[r]);
-          }
-        }
         if constexpr (C::TACC) {
           // (the exchange inside the transforms fenced the stores of the previous row)
           uint32_t w32[32], w16[16];
@@ -606,36 +572,12 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       } else {
         FFT::run(vd, fa, tw_s, tau, bar_id);
       }
-#ifdef E3_ISSUE_LATE
-      if (pleft > 0) issue();
-#endif
       if (HAS_D) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           S1[r] = f2_add(S1[r], vd[r]);
           S2[r] = fmaf(f2_lo(vd[r]), f2_lo(vd[r]), fmaf(f2_hi(vd[r]), f2_hi(vd[r]), S2[r]));
         }
-      }
-      if constexpr (C::TACC10) {
-        if (ci0 + ROWS >= ng) {  // the time closes with this row
-          uint32_t pw[8];
-          tm_ld_w8(tm_a + T10_PW, pw);
-          tm_wait_ld();
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            pw[r] = __float_as_uint(__uint_as_float(pw[r]) + f2_hsum(f2_mul(Sn1[r], Sn1[r])));
-            Sn1[r] = 0ull;
-          }
-          tm_st_w8(tm_a + T10_PW, pw);
-        }
-        uint32_t w16[16], w8[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          w16[2 * r] = (uint32_t)Sn1[r]; w16[2 * r + 1] = (uint32_t)(Sn1[r] >> 32);
-          w8[r] = __float_as_uint(Sn2[r]);
-        }
-        tm_st_w16(tm_a + T10_S1, w16);
-        tm_st_w8(tm_a + T10_S2, w8);
       }
       if constexpr (C::TACC) {
         if (ci0 + ROWS >= ng) {  // the time closes with this row: P += |sum over the group's rows|^2
@@ -669,18 +611,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (T64) {
         // a = nsample^-1/2 in fp64: the fp32 approximation (2 ulp) and one Newton step (-> 1e-13)
         const double itd = (tint > 0.f) ? 1.0 / (double)tint : 0.0;
-        if constexpr (C::TACC10) {
-          uint32_t w32[32], w16[16];
-          tm_ld_w32(tm_a + T10_AB, w32);
-          tm_ld_w16(tm_a + T10_C, w16);
-          tm_wait_ld();
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            dA[r] = __longlong_as_double((long long)f2_from_words(w32[2 * r], w32[2 * r + 1]));
-            dB[r] = __longlong_as_double((long long)f2_from_words(w32[16 + 2 * r], w32[16 + 2 * r + 1]));
-            dC[r] = __longlong_as_double((long long)f2_from_words(w16[2 * r], w16[2 * r + 1]));
-          }
-        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const double nvd = (double)ns_s[TPR * r], y0 = (double)av[r];
@@ -690,22 +620,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           dA[r] += a;
           dB[r] += ab;
           dC[r] = fma(a, ab, dC[r]);
-        }
-        if constexpr (C::TACC10) {
-          // at the close of a time the sums stay in registers for the contraction below and zeros go back
-          const bool closing = ci0 + ROWS >= ng;
-          uint32_t w32[32], w16[16];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const unsigned long long ba = closing ? 0ull : (unsigned long long)__double_as_longlong(dA[r]);
-            const unsigned long long bb = closing ? 0ull : (unsigned long long)__double_as_longlong(dB[r]);
-            const unsigned long long bc = closing ? 0ull : (unsigned long long)__double_as_longlong(dC[r]);
-            w32[2 * r] = (uint32_t)ba; w32[2 * r + 1] = (uint32_t)(ba >> 32);
-            w32[16 + 2 * r] = (uint32_t)bb; w32[16 + 2 * r + 1] = (uint32_t)(bb >> 32);
-            w16[2 * r] = (uint32_t)bc; w16[2 * r + 1] = (uint32_t)(bc >> 32);
-          }
-          tm_st_w32(tm_a + T10_AB, w32);
-          tm_st_w16(tm_a + T10_C, w16);
         }
         if (team_any<TEAM>(active && !all_ok, bar_id)) {
           if (!dirty_time) {
@@ -740,7 +654,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         ++it_off;
         ++rid_t;
 #pragma unroll
-        for (int r = 0; r < 8 && !C::TACC && !C::TACC10; ++r) {  // P += |sum over the group's rows|^2
+        for (int r = 0; r < 8 && !C::TACC; ++r) {  // P += |sum over the group's rows|^2
           f2 sd = S1[r], sn = Sn1[r];
 #pragma unroll
           for (int off = TPR; off < 32; off <<= 1) {
@@ -878,20 +792,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 
     // ---- flush the item: fp64 atomics, fftshift as an index rotation -------------
     uint32_t pwt[16];
-    if constexpr (C::TACC10) {
-      uint32_t w8[8], p8[8];
-      tm_wait_st();
-      tm_ld_w8(tm_a + T10_S2, w8);
-      tm_ld_w8(tm_a + T10_PW, p8);
-      tm_wait_ld();
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        Sn2[r] = __uint_as_float(w8[r]);
-        pwt[8 + r] = p8[r];
-      }
-      const uint32_t z8[8] = {};
-      tm_st_w8(tm_a + T10_PW, z8);
-    }
     if constexpr (C::TACC) {
       uint32_t w16[16];
       tm_wait_st();
@@ -923,9 +823,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         }
         if (HAS_N) {
           atomicAdd(P.noise_all + obase + kshift,
-                    (double)((C::TACC || C::TACC10) ? __uint_as_float(pwt[8 + r]) : pw_s[N + tau + TPR * r]));
+                    (double)(C::TACC ? __uint_as_float(pwt[8 + r]) : pw_s[N + tau + TPR * r]));
           atomicAdd(P.noise_auto + obase + kshift, (double)sn2);
-          if (!C::TACC && !C::TACC10) pw_s[N + tau + TPR * r] = 0.f;
+          if (!C::TACC) pw_s[N + tau + TPR * r] = 0.f;
         }
       }
     }

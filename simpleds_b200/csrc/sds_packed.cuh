@@ -542,9 +542,7 @@ template <int N> struct TeamFftX {
     if constexpr (TM && P == NPASS - 2) {
       f2 wn[7];
       load_tw<P + 1>(wn, tw, tau);  // (the last pass's section is stored permuted: tm_tw_src)
-#ifndef SDS_TM_NOWAIT
       tm_wait_st();
-#endif
       // loaded slot (tau4 t2 tau3) is logical slot (tau4 tau3 t2): 1 <-> 2, 5 <-> 6
       tm_ld4(tm, a[0], a[2], a[1], a[3]);
       tm_ld4(tm + (16u << 16), a[4], a[6], a[5], a[7]);
