@@ -415,6 +415,14 @@ engine_kernel(const __grid_constant__ EngineParams P) {
           S2[r] += v[r].x * v[r].x + v[r].y * v[r].y;
         }
         if constexpr (C::TACC) {
+          uint32_t w16[16];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const unsigned long long b2 = TeamFftD256::bits((double)S2[r]);
+            w16[2 * r] = (uint32_t)b2; w16[2 * r + 1] = (uint32_t)(b2 >> 32);
+          }
+          tm_st_w16(tm_a + TC_S2, w16);
+          // (two self-contained branches: merging them costs register moves on every row)
           if (ci0 + ROWS >= ng) {  // the time closes with this row
             uint32_t pw[16];
             tm_ld_w16(tm_a + TC_PW, pw);
@@ -425,21 +433,20 @@ engine_kernel(const __grid_constant__ EngineParams P) {
                                 (double)(S1[r].x * S1[r].x + S1[r].y * S1[r].y);
               const unsigned long long b = TeamFftD256::bits(pv);
               pw[2 * r] = (uint32_t)b; pw[2 * r + 1] = (uint32_t)(b >> 32);
-              S1[r] = {(T)0, (T)0};
             }
             tm_st_w16(tm_a + TC_PW, pw);
-          }
-          uint32_t w32[32], w16[16];
+            const uint32_t z32[32] = {};
+            tm_st_w32(tm_a + TC_S1, z32);
+          } else {
+            uint32_t w32[32];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const unsigned long long bx = TeamFftD256::bits((double)S1[r].x), by = TeamFftD256::bits((double)S1[r].y),
-                                     b2 = TeamFftD256::bits((double)S2[r]);
-            w32[4 * r] = (uint32_t)bx; w32[4 * r + 1] = (uint32_t)(bx >> 32);
-            w32[4 * r + 2] = (uint32_t)by; w32[4 * r + 3] = (uint32_t)(by >> 32);
-            w16[2 * r] = (uint32_t)b2; w16[2 * r + 1] = (uint32_t)(b2 >> 32);
+            for (int r = 0; r < 8; ++r) {
+              const unsigned long long bx = TeamFftD256::bits((double)S1[r].x), by = TeamFftD256::bits((double)S1[r].y);
+              w32[4 * r] = (uint32_t)bx; w32[4 * r + 1] = (uint32_t)(bx >> 32);
+              w32[4 * r + 2] = (uint32_t)by; w32[4 * r + 3] = (uint32_t)(by >> 32);
+            }
+            tm_st_w32(tm_a + TC_S1, w32);
           }
-          tm_st_w32(tm_a + TC_S1, w32);
-          tm_st_w16(tm_a + TC_S2, w16);
         }
       }
 

@@ -580,6 +580,14 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         }
       }
       if constexpr (C::TACC) {
+        uint32_t w16[16];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          w16[r] = __float_as_uint(S2[r]);
+          w16[8 + r] = __float_as_uint(Sn2[r]);
+        }
+        tm_st_w16(tm_a + TC_S2, w16);
+        // (two self-contained branches: merging them costs a register move per accumulator on every row)
         if (ci0 + ROWS >= ng) {  // the time closes with this row: P += |sum over the group's rows|^2
           uint32_t pw[16];
           tm_ld_w16(tm_a + TC_PW, pw);
@@ -588,20 +596,19 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           for (int r = 0; r < 8; ++r) {
             pw[r] = __float_as_uint(__uint_as_float(pw[r]) + f2_hsum(f2_mul(S1[r], S1[r])));
             pw[8 + r] = __float_as_uint(__uint_as_float(pw[8 + r]) + f2_hsum(f2_mul(Sn1[r], Sn1[r])));
-            S1[r] = Sn1[r] = 0ull;
           }
           tm_st_w16(tm_a + TC_PW, pw);
-        }
-        uint32_t w32[32], w16[16];
+          const uint32_t z32[32] = {};
+          tm_st_w32(tm_a + TC_S1, z32);
+        } else {
+          uint32_t w32[32];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          w32[2 * r] = (uint32_t)S1[r]; w32[2 * r + 1] = (uint32_t)(S1[r] >> 32);
-          w32[16 + 2 * r] = (uint32_t)Sn1[r]; w32[16 + 2 * r + 1] = (uint32_t)(Sn1[r] >> 32);
-          w16[r] = __float_as_uint(S2[r]);
-          w16[8 + r] = __float_as_uint(Sn2[r]);
+          for (int r = 0; r < 8; ++r) {
+            w32[2 * r] = (uint32_t)S1[r]; w32[2 * r + 1] = (uint32_t)(S1[r] >> 32);
+            w32[16 + 2 * r] = (uint32_t)Sn1[r]; w32[16 + 2 * r + 1] = (uint32_t)(Sn1[r] >> 32);
+          }
+          tm_st_w32(tm_a + TC_S1, w32);
         }
-        tm_st_w32(tm_a + TC_S1, w32);
-        tm_st_w16(tm_a + TC_S2, w16);
       }
 
       if (HAS_T && !C::F4) {
