@@ -225,7 +225,11 @@ typedef struct sds_engine_desc {
  * nuv == 1 the pair sums sum_ij x_i conj(x_j) = |sum_i x_i|^2 are real),
  * thermal_all/thermal_auto real [ngroup][nspw][npol] (already including the
  * 1/(npol sqrt2) and 1e-6 factors and the per-baseline 1/t_int).
- * workspace: sds_engine_workspace_bytes() bytes of device scratch. */
+ * workspace: sds_engine_workspace_bytes() bytes of device scratch.
+ * Device resources: besides registers and shared memory the power-of-two kernels of this call allocate
+ * TENSOR MEMORY (tcgen05.alloc, 32-256 columns per CTA, freed before the CTA exits) for the exchanges
+ * of the transform and for their accumulators; two such kernels on one SM wait for each other's
+ * columns, they do not fail. */
 int64_t sds_engine_workspace_bytes(const sds_plan *plan, const sds_engine_desc *desc);
 int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void *vis,
                    const uint8_t *flags, const float *nsample, const float *int_time,
