@@ -678,9 +678,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         if (HAS_T) {
           const double *wlp = P.wl + ((int64_t)s * P.npol + p) * N + tau;
           const double *wrp = P.wr + ((int64_t)s * P.npol + p) * N + tau;
-          // the right end of a panel is the next channel: another thread's sums, through this
-          // row's exchange buffers ((A, B) pairs in the first, C in the second)
-          team_sync<TEAM>(bar_id);  // the step's last transform reads are done
           float Ar[8], Br[8], Cr[8], Ap[8], Bp[8], Cp[8];
           if constexpr (C::TACC) {  // (stored before this row's exchange, which fenced them)
             uint32_t w16[16], w8[8];
@@ -704,6 +701,19 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
             Br[2 * m] = f2_lo(tB[m]); Br[2 * m + 1] = f2_hi(tB[m]);
             Cr[2 * m] = f2_lo(tC[m]); Cr[2 * m + 1] = f2_hi(tC[m]);
           }
+          if (ROWS == 1 && !dirty_time) {
+            // no invalid sample in this time: every panel counts, and the left-end weight of panel c and the
+            // right-end weight of panel c - 1 multiply the same sums -- one weight per channel, no neighbour
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const double w = __ldg(wlp + TPR * r) + ((r > 0 || tau > 0) ? __ldg(wrp + TPR * r - 1) : 0.0);
+              th_all_acc += w * (double)(Ar[r] * Br[r]);
+              th_auto_acc += w * (double)Cr[r];
+            }
+          } else {
+          // the right end of a panel is the next channel: another thread's sums, through this
+          // row's exchange buffers ((A, B) pairs in the first, C in the second)
+          team_sync<TEAM>(bar_id);  // the step's last transform reads are done
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             sts_f2(xa + 8u * (uint32_t)(tau + TPR * r), f2_make(Ar[r], Br[r]));
@@ -742,6 +752,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
             if (sub == 0)
               th_all_acc += l * (double)(f2_lo(ab) * f2_lo(bb)) + rr * (double)(f2_hi(ab) * f2_hi(bb));
             th_auto_acc += l * (double)Cr[r] + rr * (double)Cp[r];
+          }
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) tA[k] = tB[k] = tC[k] = 0ull;
