@@ -177,6 +177,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     tm_fence_after();
     const uint32_t warp = threadIdx.x >> 5;
     tm_a = tm_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)C::TM_WCOLS;
+    tm_a = __shfl_sync(0xffffffffu, tm_a, 0);  // warp-uniform for the compiler too: lives in a uniform register
   }
   // tensor-memory columns of the accumulators (TACC), after the 32 columns of the exchange:
   // [32, 64) S1, Sn1 | [64, 80) S2, Sn2 | [80, 104) tA, tB, tC | [104, 120) per-time |S1|^2 sums
@@ -396,8 +397,10 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           const float nv = ns_s[TPR * r];
           const bool ok = active && nv > 0.f;
           av[r] = ok ? fast_rsqrt(nv) : 0.f;
-          all_ok = all_ok && ok;
         }
+        // every sample valid <=> the smallest nsample^-1/2 is positive (three-input minima: four instructions)
+        const float m0 = fminf(fminf(av[0], av[1]), av[2]), m1 = fminf(fminf(av[3], av[4]), av[5]);
+        all_ok = fminf(fminf(m0, m1), fminf(av[6], av[7])) > 0.f;
       }
 
       // ---- data leg: (1 - flag) * taper * delta_f ; noise leg: draw * sigma(nsample, t_int) --
