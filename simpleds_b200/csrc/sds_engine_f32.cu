@@ -140,7 +140,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   asm volatile("" : "+r"(xa));
   asm volatile("" : "+r"(wb_a));
 #endif
-  const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : FFT::make_addr(xa, tau);
+  const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : C::TM1 ? FFT::make_addr_p1(xa, tau) : FFT::make_addr(xa, tau);
   // four-step: the addresses of the warp-local 256-point transform in the warp's region of the row's buffer
   const typename TeamFftX<256>::Addr fa4 =
       TeamFftX<256>::make_addr_il(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION, tau & 31);

@@ -398,6 +398,9 @@ template <int N> struct TeamFftX {
       if constexpr (TM1 && P == NPASS - 2) {
         tm_st8(tm, x[brev(0, 3)], x[brev(1, 3)], x[brev(2, 3)], x[brev(3, 3)], x[brev(4, 3)], x[brev(5, 3)],
                x[brev(6, 3)], x[brev(7, 3)]);
+      } else if constexpr (TM1 && P < NPASS - 1) {
+        // (TM1: 8-byte slots padded j + (j >> 4): additive like the pair's layout, immediates only)
+        tm1_store<P, 0>(A.st[P], x);
       } else if constexpr (P < NPASS - 1) {
 #pragma unroll
         for (int p = 0; p < R; ++p) {
@@ -420,6 +423,13 @@ template <int N> struct TeamFftX {
       tm_ld4(tm, a[0], a[2], a[1], a[3]);  // (slot renaming: see pass_il)
       tm_ld4(tm + (16u << 16), a[4], a[6], a[5], a[7]);
       tm_wait_ld();
+      pass<P + 1, TWO, TM1>(a, b, A, tw, tau, bar, wn, tm);
+    } else if constexpr (TM1 && P < NPASS - 1) {
+      f2 wn[7];
+      load_tw<P + 1>(wn, tw, tau);
+      team_sync<WORKER>(bar);
+      tm1_load<0>(A.ld, a);
+      if constexpr (P < NPASS - 2) team_sync<WORKER>(bar);
       pass<P + 1, TWO, TM1>(a, b, A, tw, tau, bar, wn, tm);
     } else if constexpr (P < NPASS - 1) {
       f2 wn[7];
@@ -447,7 +457,34 @@ template <int N> struct TeamFftX {
     const f2 w0[7] = {};
     pass<0, false>(a, a, A, tw, tau, bar, w0);
   }
-  // one transform, last exchange through tensor memory (TM_OK lengths); bins of lane l on return: tm_tau(l) + TPR r
+  // One transform whose last exchange goes through tensor memory: its shared-memory exchanges use 8-byte
+  // slots at j + (j >> 4) -- conflict-free per half warp for the stores and loads of the schedule (checked
+  // for N = 256) and additive over the index split, so every access is [register + immediate].
+  static __host__ __device__ constexpr int p1_pad(int j) { return j + (j >> 4); }
+  static constexpr int P1_BYTES = 8 * (N + N / 16);
+  static __device__ __forceinline__ Addr make_addr_p1(uint32_t xa, int tau) {
+    Addr A;
+#pragma unroll
+    for (int p = 0; p < NST; ++p) {
+      const int NS = fft_ns(N, p), R = fft_radix(N, p);
+      A.st[p] = xa + 8u * (uint32_t)p1_pad((tau / NS) * (NS * R) + (tau % NS));
+    }
+    A.ld = xa + 8u * (uint32_t)p1_pad(tau);
+    return A;
+  }
+  template <int P, int p> static __device__ __forceinline__ void tm1_store(uint32_t st, const f2 (&x)[8]) {
+    if constexpr (p < 8) {
+      sts_f2_off<8 * p1_pad(p * fft_ns(N, P))>(st, x[brev(p, 3)]);
+      tm1_store<P, p + 1>(st, x);
+    }
+  }
+  template <int r> static __device__ __forceinline__ void tm1_load(uint32_t ld, f2 (&a)[8]) {
+    if constexpr (r < 8) {
+      a[r] = lds_f2_off<8 * p1_pad(TPR * r)>(ld);
+      tm1_load<r + 1>(ld, a);
+    }
+  }
+  // A: make_addr_p1; tm: 16 tensor-memory columns; bins of lane l on return: tm_tau(l) + TPR r
   static __device__ __forceinline__ void run_tm1(f2 (&a)[8], const Addr &A, const f2 *__restrict__ tw,
                                                  int tau, int bar, uint32_t tm) {
     const f2 w0[7] = {};
