@@ -32,9 +32,6 @@ namespace sds {
 #ifndef E3_F4
 #define E3_F4 1  // N = 2048: one team-wide exchange, then one 256-point transform per warp (TeamFft8x256)
 #endif
-#ifndef E3_F4_SPLIT
-#define E3_F4_SPLIT 1  // four-step: arrive / wait instead of a blocking team barrier
-#endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
 #endif
@@ -488,7 +485,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           tm_st_w8(tm_a + TC_T + 16, w8);
         }
       };
-      if (HAS_T && !(C::F4 && E3_F4_SPLIT)) thermal_sums();
+      if (HAS_T && !C::F4) thermal_sums();
       // a panel counts only when both of its ends are valid (masked_invalid, ds.py:3697); a row
       // with any invalid sample books what the full sums above contain but the panel must not
       auto book_deficits = [&]() {
@@ -519,7 +516,6 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           mbar_wait_a(free_a, par_f);  // every warp has made its last read of the previous row's buffer
           par_f ^= 1u;
           TeamFft8x256::store(vd, vn, xa, tau);
-#if E3_F4_SPLIT
           // the row's ONE team-wide synchronisation as an arrive / wait pair on an mbarrier (one arrival
           // per warp), with the thermal sums in between; the "some sample of the row is invalid" vote
           // travels as the row's sequence number in one of two flag words (a word is rewritten two rows
@@ -534,20 +530,18 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
             }
           }
           if (HAS_T) thermal_sums();
+          f2 tw4[8];
+          TeamFft8x256::twiddles(tw4, tw_s, tau);
           mbar_wait_a(stored_a, par_s);
           par_s ^= 1u;
           dirty_row = lds_u32(flag_a + 4u * (seq_f4 & 1u)) == seq_f4;
-#else
-          // the row's ONE team-wide barrier, carrying the "some sample of the row is invalid" vote
-          dirty_row = team_any<TEAM>(active && !all_ok, bar_id);
-#endif
           if (HAS_T && dirty_row) {  // rare: the booking re-reads nsample of the staged row
             book_deficits();
             team_sync<TEAM>(bar_id);
           }
           // all warps have consumed this row's slot: refill it (two rows ahead)
           if (pleft > 0) issue();
-          TeamFft8x256::back(vd, vn, xa, fa4, tw_s, tau, bar_id, tm_a, free_a);
+          TeamFft8x256::back(vd, vn, tw4, xa, fa4, tw_s, tau, bar_id, tm_a, free_a);
         } else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);

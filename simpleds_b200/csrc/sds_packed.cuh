@@ -694,13 +694,17 @@ struct TeamFft8x256 {
   static __device__ __forceinline__ void store(const f2 (&a)[8], const f2 (&b)[8], uint32_t xT, int tau) {
     store_t<0>(xT + 16u * (uint32_t)tau, a, b);
   }
-  static __device__ __forceinline__ void back(f2 (&a)[8], f2 (&b)[8], uint32_t xT, const typename F256::Addr &A,
-                                              const f2 *__restrict__ tw, int tau, int bar, uint32_t tm,
-                                              uint32_t free_bar) {
+  // the twiddles W_2048^(n2 k1) of the values this thread will own after the transposition (loaded in
+  // the shadow of the team-wide exchange)
+  static __device__ __forceinline__ void twiddles(f2 (&t)[8], const f2 *__restrict__ tw, int tau) {
     const int w = tau >> 5, lane = tau & 31;
-    f2 t[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) t[r] = tw[w * 256 + lane + 32 * r];
+  }
+  static __device__ __forceinline__ void back(f2 (&a)[8], f2 (&b)[8], const f2 (&t)[8], uint32_t xT,
+                                              const typename F256::Addr &A, const f2 *__restrict__ tw, int tau,
+                                              int bar, uint32_t tm, uint32_t free_bar) {
+    const int w = tau >> 5, lane = tau & 31;
     load_t<0>(xT + (uint32_t)w * REGION + 16u * (uint32_t)lane, a, b);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
