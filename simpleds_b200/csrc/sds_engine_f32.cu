@@ -87,7 +87,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
                                         ? TeamFft8x256::TW_TOTAL : fft_tw_total(N);
   static constexpr int TW_BYTES = ((TW_ENTRIES * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
-  static constexpr int HEAD = 192;
+  static constexpr int HEAD = 448;  // 64 B barriers | 128 B t_int^-1/2 of 32 steps | 256 B 1 / t_int in fp64 (T64)
   static constexpr int WORKER_BYTES = HEAD + STAGES * SLOT + (TACC ? 0 : 8 * N);
   // XALIGN bytes of slack in front: the exchange region is aligned at run time
   static constexpr int SMEM = XALIGN + XREGION + TW_BYTES + NWORKER * WORKER_BYTES;
@@ -144,7 +144,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   unsigned char *wbase = reinterpret_cast<unsigned char *>(__cvta_shared_to_generic(wb_a));
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + C::HEAD;
-  const uint32_t tv_a = wb_a + 64;  // [32] floats: integration times of the next steps
+  const uint32_t tv_a = wb_a + 64;  // [32] floats t_int^-1/2 of the next steps, then [32] doubles 1 / t_int (T64)
   const uint32_t full_a = wb_a, stages_a = wb_a + C::HEAD;  // shared-space addresses
   const uint32_t free_a = wb_a + 32;  // four-step: the buffer-release barrier
   uint32_t par_f = 1u;                // its phase parity (a fresh barrier passes a wait on parity 1)
@@ -329,7 +329,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     if (!TV && (HAS_N || HAS_T || T64))
       tint_next = __ldg(P.int_time + it_off + (int64_t)((ROWS == 1 || sub < ng) ? sub : 0) * P.ntime);
     // one row per step: entry (f & 31) of a small shared-memory ring holds the integration time of
-    // step f of the item (t_int^-1/2 unless the fp64 thermal sums need the value itself); the half of
+    // step f of the item (t_int^-1/2; the fp64 thermal sums also keep 1 / t_int in fp64 there); the half of
     // the ring that is not being consumed is refilled every 16 steps, 16 to 31 steps ahead of its use,
     // and a row takes its value with one broadcast load instead of an address computation and an L2 load
     auto tv_fill = [&](int f) {
@@ -342,7 +342,13 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         if (ii < 0) { ii += ng; --tt; }
         if (ii >= ng) { ii -= ng; ++tt; }
         v = __ldg(P.int_time + it0 + (int64_t)ii * P.ntime + tt);
-        if (!T64) v = v > 0.f ? fast_rsqrt(v) : 0.f;
+        if (T64) {
+          const double id = v > 0.f ? 1.0 / (double)v : 0.0;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(tv_a + 128u + 8u * (uint32_t)(f & 31)), "d"(id) : "memory");
+        }
+        v = v > 0.f ? fast_rsqrt(v) : 0.f;
+      } else if (T64) {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(tv_a + 128u + 8u * (uint32_t)(f & 31)), "d"(0.0) : "memory");
       }
       sts_f32(tv_a + 4u * (uint32_t)(f & 31), v);
     };
@@ -360,11 +366,13 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       const bool active = ROWS == 1 || i < ng;
       const int ia = active ? i : 0;
       float tint = tint_next;
+      double itd_ring = 0.0;
       if constexpr (TV) {
         // (every warp of a team writes the same values; the step's team sync orders them before the reads)
         if ((step & 15) == 0 && (((int)threadIdx.x ^ step) & 16) != 0)
           tv_fill(step + 16 + (int)(threadIdx.x & 15u));
         tint = lds_f32(tv_a + 4u * (uint32_t)(step & 31));
+        if (T64) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(itd_ring) : "r"(tv_a + 128u + 8u * (uint32_t)(step & 31)) : "memory");
       }
       if (!TV && (HAS_N || HAS_T || T64) && step + 1 < nsteps) {
         const bool wrap = ci0 + ROWS >= ng;
@@ -383,7 +391,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       const unsigned char *fl_s = row + C::VISB + 4 * N + tau;
 
       // rt = t_int^-1/2, itv = 1 / t_int (0 where the integration time is not positive)
-      const float rt = (TV && !T64) ? tint : (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
+      const float rt = TV ? tint : (tint > 0.f) ? fast_rsqrt(tint) : 0.f;
       const float itv = rt * rt;
       // a = nsample^-1/2 (0 where invalid): shared by the noise amplitude and the thermal sums
       float av[8];
@@ -614,7 +622,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 
       if (T64) {
         // a = nsample^-1/2 in fp64: the fp32 approximation (2 ulp) and one Newton step (-> 1e-13)
-        const double itd = (tint > 0.f) ? 1.0 / (double)tint : 0.0;
+        const double itd = TV ? itd_ring : (tint > 0.f) ? 1.0 / (double)tint : 0.0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const double nvd = (double)ns_s[TPR * r], y0 = (double)av[r];
