@@ -251,6 +251,22 @@ int sds_engine_run(const sds_plan *plan, const sds_engine_desc *desc, const void
  * (delay_spectrum.py:3655-3707: N_ij = sqrt(n1_j n2_i), integration time of baseline j) rides in the
  * noise launch: thermal_coef != NULL needs noise_mode 1 or 2. */
 
+/* Means over ordered baseline pairs and times from the sums sds_engine_run accumulates (tutorial cell 41:
+ * power.mean over (i, j, t); utils.py:281-331 remove_auto_correlations for the i != j variant), the six
+ * outputs in ONE launch:
+ *   x_all     = all  / (n n T),
+ *   x_noautos = (all - auto) / (n (n - 1) T)      (NaN for a group of one baseline: no cross pairs)
+ * with n = group_size[g] and T = times_done[g] (the group's count of accumulated times, which travels
+ * with the sums through a multi-GPU reduce; a group that saw no time gives NaN) or ntimes when > 0.
+ * rows_per_group = nspw * npol; row_len = values per row of the pair sums (N, or 2 N for the complex
+ * sums of two data sets).  Any input / output pair may be NULL together. */
+int sds_engine_means(int32_t ngroup, int32_t rows_per_group, int32_t row_len, const int32_t *group_size,
+                     const double *times_done, double ntimes, const double *pow_all,
+                     const double *pow_auto, const double *noise_all, const double *noise_auto,
+                     const double *thermal_all, const double *thermal_auto, double *power_all,
+                     double *power_noautos, double *noise_power_all, double *noise_power_noautos,
+                     double *thermal_mean_all, double *thermal_mean_noautos, sds_stream stream);
+
 /* ---- downstream estimators on the (averaged) spectra: SURVEY 8(f3) ----------------------
  * All arrays are C-ordered and viewed as (outer, n, inner) around the reduced / folded /
  * resampled axis; values are fp64 (real) or complex128 (interleaved, dtype = SDS_F64 / SDS_C128). */

@@ -69,6 +69,7 @@ _SIGNATURES = {
                                    _vp, _i32, _i32, _vp, _vp, _vp]),
     "sds_engine_workspace_bytes": (_i64, [_vp, C.POINTER(EngineDesc)]),
     "sds_engine_run": (_i32, [_vp, C.POINTER(EngineDesc)] + [_vp] * 17 + [_vp, C.POINTER(C.c_int32)]),
+    "sds_engine_means": (_i32, [_i32, _i32, _i32, _vp, _vp, _dbl] + [_vp] * 12 + [_vp]),
     "sds_weighted_average": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "sds_fold_along_delay": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
                                     _vp, _vp, _vp]),

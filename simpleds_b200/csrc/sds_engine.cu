@@ -897,3 +897,68 @@ extern "C" int sds_engine_run(const sds_plan *plan, const sds_engine_desc *d, co
   return rc;
 }
 
+
+// ---- means over pairs and times from the accumulated sums (sds.h: sds_engine_means) ---------------
+namespace sds {
+__global__ void engine_means_kernel(int rows_per_group, int row_len, const int32_t *__restrict__ group_size,
+                                    const double *__restrict__ times_done, double ntimes,
+                                    const double *__restrict__ pow_all, const double *__restrict__ pow_auto,
+                                    const double *__restrict__ noise_all, const double *__restrict__ noise_auto,
+                                    const double *__restrict__ th_all, const double *__restrict__ th_auto,
+                                    double *__restrict__ o_pa, double *__restrict__ o_pn, double *__restrict__ o_na,
+                                    double *__restrict__ o_nn, double *__restrict__ o_ta, double *__restrict__ o_tn) {
+  const int64_t row = blockIdx.x;  // (group, spw, pol)
+  const int g = (int)(row / rows_per_group);
+  const double n = (double)group_size[g];
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double T = ntimes > 0.0 ? ntimes : times_done[g];
+  if (!(T > 0.0)) T = nan;
+  const double f_all = 1.0 / (n * n * T);
+  const double f_no = n > 1.0 ? 1.0 / (n * (n - 1.0) * T) : nan;
+  for (int k = threadIdx.x; k < row_len; k += blockDim.x) {
+    const int64_t e = row * row_len + k;
+    if (pow_all) {
+      const double a = pow_all[e];
+      o_pa[e] = a * f_all;
+      o_pn[e] = n > 1.0 ? (a - pow_auto[e]) * f_no : nan;
+    }
+    if (noise_all) {
+      const double a = noise_all[e];
+      o_na[e] = a * f_all;
+      o_nn[e] = n > 1.0 ? (a - noise_auto[e]) * f_no : nan;
+    }
+  }
+  if (th_all && threadIdx.x == 0) {
+    const double a = th_all[row];
+    o_ta[row] = a * f_all;
+    o_tn[row] = n > 1.0 ? (a - th_auto[row]) * f_no : nan;
+  }
+}
+}  // namespace sds
+
+extern "C" int sds_engine_means(int32_t ngroup, int32_t rows_per_group, int32_t row_len, const int32_t *group_size,
+                                const double *times_done, double ntimes, const double *pow_all,
+                                const double *pow_auto, const double *noise_all, const double *noise_auto,
+                                const double *thermal_all, const double *thermal_auto, double *power_all,
+                                double *power_noautos, double *noise_power_all, double *noise_power_noautos,
+                                double *thermal_mean_all, double *thermal_mean_noautos, sds_stream stream) {
+  using namespace sds;
+  if (ngroup < 0 || rows_per_group <= 0 || row_len <= 0 || !group_size || (!times_done && !(ntimes > 0.0))) {
+    set_error("sds_engine_means: bad arguments");
+    return SDS_EINVAL;
+  }
+  if ((pow_all && (!pow_auto || !power_all || !power_noautos)) ||
+      (noise_all && (!noise_auto || !noise_power_all || !noise_power_noautos)) ||
+      (thermal_all && (!thermal_auto || !thermal_mean_all || !thermal_mean_noautos))) {
+    set_error("sds_engine_means: a sum needs its auto sum and both outputs");
+    return SDS_EINVAL;
+  }
+  if (ngroup == 0) return SDS_OK;
+  const int64_t rows = (int64_t)ngroup * rows_per_group;
+  engine_means_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(
+      rows_per_group, row_len, group_size, times_done, ntimes, pow_all, pow_auto, noise_all, noise_auto, thermal_all,
+      thermal_auto, power_all, power_noautos, noise_power_all, noise_power_noautos, thermal_mean_all,
+      thermal_mean_noautos);
+  SDS_LAUNCH_CHECK("engine_means_kernel");
+  return SDS_OK;
+}

@@ -470,19 +470,25 @@ class RedundantPipeline:
 
         ``*_all``: every ordered pair (i, j), autos included (tutorial cell 41);
         ``*_noautos``: i != j (utils.remove_auto_correlations); NaN for 1-baseline groups."""
-        n = torch.as_tensor(self.group_sizes, dtype=torch.float64, device=self.device)
-        # per-group count of accumulated times (NaN for a group that saw none), or the caller's
-        tg = torch.where(self.times_done > 0, self.times_done, torch.full_like(self.times_done, float("nan")))
-        if ntimes is not None:
-            tg = torch.full_like(self.times_done, float(ntimes))
-        n4, n3, T4, T3 = n.view(-1, 1, 1, 1), n.view(-1, 1, 1), tg.view(-1, 1, 1, 1), tg.view(-1, 1, 1)
+        # one launch for the six means (sds_engine_means; the per-group time counts are read on the device)
+        lib = _lib.load()
+        if getattr(self, "_group_sizes_dev", None) is None:
+            self._group_sizes_dev = torch.as_tensor(self.group_sizes.astype(np.int32), device=self.device)
         out = {}
-        nan = torch.full((), float("nan"), dtype=torch.float64, device=self.device)  # one baseline: no cross pairs
-        for key, a, b in (("power", self.pow_all, self.pow_auto), ("noise_power", self.noise_all, self.noise_auto)):
-            out[key + "_all"] = a / (n4 * n4 * T4)
-            out[key + "_noautos"] = torch.where(n4 > 1, (a - b) / (n4 * (n4 - 1) * T4), nan)
-        out["thermal_all"] = self.thermal_all / (n3 * n3 * T3)
-        out["thermal_noautos"] = torch.where(n3 > 1, (self.thermal_all - self.thermal_auto) / (n3 * (n3 - 1) * T3), nan)
+        names = ("power_all", "power_noautos", "noise_power_all", "noise_power_noautos")
+        for k in names:
+            out[k] = torch.empty_like(self.pow_all)
+        out["thermal_all"] = torch.empty_like(self.thermal_all)
+        out["thermal_noautos"] = torch.empty_like(self.thermal_all)
+        row_len = self.nfreq * (2 if self.pow_all.is_complex() else 1)
+        check(lib.sds_engine_means(
+            self.ngroup, self.nspw * self.npol, row_len, ptr(self._group_sizes_dev), ptr(self.times_done),
+            float(ntimes) if ntimes is not None else 0.0,
+            ptr(self.pow_all), ptr(self.pow_auto), ptr(self.noise_all), ptr(self.noise_auto),
+            ptr(self.thermal_all), ptr(self.thermal_auto),
+            ptr(out["power_all"]), ptr(out["power_noautos"]), ptr(out["noise_power_all"]),
+            ptr(out["noise_power_noautos"]), ptr(out["thermal_all"]), ptr(out["thermal_noautos"]),
+            stream_ptr()), "sds_engine_means")
         out["delay_array_ns"] = self.delay_array_ns
         return out
 

@@ -372,3 +372,49 @@ def test_fused_engine_two_data_sets_match_oracle(cuda_device, N, nwin):
                           precision="complex128", nuv=2).process(
             torch.as_tensor(vis, device=dev), torch.as_tensor(flags, device=dev), torch.as_tensor(ns, device=dev),
             torch.as_tensor(a["int_time"], device=dev))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_engine_means_match_the_numpy_formulas(cuda_device, cplx):
+    """sds_engine_means (one launch) against the mean over ordered pairs and times written out in numpy
+    (tutorial cell 41; utils.remove_auto_correlations): groups of 1 baseline (no cross pairs: NaN), a group
+    that saw no time (NaN), per-group time counts, the ntimes override, complex sums of two data sets."""
+    import ctypes as C
+
+    from simpleds_b200 import _lib
+    from simpleds_b200._lib import check, ptr, stream_ptr
+
+    rng = np.random.default_rng(5)
+    G, S, P, N = 5, 2, 2, 64
+    sizes = np.array([4, 1, 7, 2, 3], np.int32)
+    tdone = np.array([3.0, 3.0, 0.0, 5.0, 3.0])
+    L = N * (2 if cplx else 1)
+    sums = {k: rng.standard_normal((G, S, P, L)) for k in ("pa", "pu", "na", "nu")}
+    th = {k: rng.standard_normal((G, S, P)) for k in ("ta", "tu")}
+    dev = cuda_device
+    d = {k: torch.as_tensor(v, device=dev) for k, v in {**sums, **th}.items()}
+    outs = {k: torch.empty_like(d["pa"]) for k in ("pa", "pn", "na", "nn")}
+    outs.update({k: torch.empty_like(d["ta"]) for k in ("ta", "tn")})
+    gs, td = torch.as_tensor(sizes, device=dev), torch.as_tensor(tdone, device=dev)
+    lib = _lib.load()
+    for ntimes in (0.0, 4.0):
+        check(lib.sds_engine_means(G, S * P, L, ptr(gs), ptr(td), ntimes, ptr(d["pa"]), ptr(d["pu"]), ptr(d["na"]),
+                                   ptr(d["nu"]), ptr(d["ta"]), ptr(d["tu"]), ptr(outs["pa"]), ptr(outs["pn"]),
+                                   ptr(outs["na"]), ptr(outs["nn"]), ptr(outs["ta"]), ptr(outs["tn"]), stream_ptr()),
+              "sds_engine_means")
+        torch.cuda.synchronize()
+        n = sizes.astype(float)
+        T = np.full(G, ntimes) if ntimes > 0 else np.where(tdone > 0, tdone, np.nan)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for a, u, oa, on, shape in (("pa", "pu", "pa", "pn", (G, 1, 1, 1)), ("na", "nu", "na", "nn", (G, 1, 1, 1)),
+                                        ("ta", "tu", "ta", "tn", (G, 1, 1))):
+                A = {**sums, **th}[a]
+                U = {**sums, **th}[u]
+                nn_, TT = n.reshape(shape), T.reshape(shape)
+                want_all = A / (nn_ * nn_ * TT)
+                want_no = np.where(nn_ > 1, (A - U) / (nn_ * (nn_ - 1) * TT), np.nan)
+                np.testing.assert_allclose(outs[oa].cpu().numpy(), want_all, rtol=1e-14, equal_nan=True)
+                np.testing.assert_allclose(outs[on].cpu().numpy(), want_no, rtol=1e-14, equal_nan=True)
+    # a sum without its partner is refused
+    assert lib.sds_engine_means(G, S * P, L, ptr(gs), ptr(td), 0.0, ptr(d["pa"]), None, None, None, None, None,
+                                ptr(outs["pa"]), ptr(outs["pn"]), None, None, None, None, stream_ptr()) != 0
