@@ -136,17 +136,24 @@ class RedundantPipeline:
         dev, shape = self.device, (self.ngroup, self.nspw, self.npol, self.nfreq)
         # with one data set (Nuv = 1) the pair sums are real: sum_ij x_i conj(x_j) = |sum_i x_i|^2;
         # with two they are (sum_i A2_i) conj(sum_j A1_j): complex
-        pdt = torch.float64 if self.nuv == 1 else torch.complex128
-        self.pow_all = torch.zeros(shape, dtype=pdt, device=dev)
-        self.pow_auto = torch.zeros(shape, dtype=pdt, device=dev)
-        self.noise_all = torch.zeros(shape, dtype=pdt, device=dev)
-        self.noise_auto = torch.zeros(shape, dtype=pdt, device=dev)
-        self.thermal_all = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
-        self.thermal_auto = torch.zeros(shape[:3], dtype=torch.float64, device=dev)
+        # ONE flat fp64 buffer holds every accumulator (zeroed with one fill, reduced over the ranks in
+        # place with one collective: reduce()); the tensors below are views of it
+        cplx = self.nuv != 1
+        npair = int(np.prod(shape)) * (2 if cplx else 1)
+        nth = int(np.prod(shape[:3]))
+        self._flat = torch.zeros(4 * npair + 2 * nth + self.ngroup, dtype=torch.float64, device=dev)
+
+        def pair_view(k):
+            v = self._flat[k * npair:(k + 1) * npair]
+            return torch.view_as_complex(v.view(*shape, 2)) if cplx else v.view(shape)
+
+        self.pow_all, self.pow_auto, self.noise_all, self.noise_auto = (pair_view(k) for k in range(4))
+        self.thermal_all = self._flat[4 * npair:4 * npair + nth].view(shape[:3])
+        self.thermal_auto = self._flat[4 * npair + nth:4 * npair + 2 * nth].view(shape[:3])
         # times accumulated per group: travels with the sums through reduce(), so that result() is
         # right whichever way the job was sharded (times split over ranks add up, groups dealt to
         # ranks are disjoint)
-        self.times_done = torch.zeros(self.ngroup, dtype=torch.float64, device=dev)
+        self.times_done = self._flat[4 * npair + 2 * nth:]
         self.ntimes_done = 0  # times this process has passed to process() (bookkeeping only)
         self._ws = None
 
@@ -454,9 +461,16 @@ class RedundantPipeline:
         collective on one flat buffer; see shard.reduce_partials).  Afterwards ``result()``
         on ``dst`` (every rank with ``all_ranks``) is the result of the whole job, whether
         the ranks split the times or the groups."""
-        from . import shard
+        import torch.distributed as dist
 
-        shard.reduce_partials(self.sums(), dst=dst, all_ranks=all_ranks)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        # the accumulators are views of one flat fp64 buffer (reset()): one collective, in place
+        # (shard.reduce_partials does the same for a dict of separate tensors)
+        if all_ranks:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        else:
+            dist.reduce(self._flat, dst=dst, op=dist.ReduceOp.SUM)
 
     # ------------------------------------------------------------------ results
     def sums(self):
