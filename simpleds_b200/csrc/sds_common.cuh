@@ -48,6 +48,30 @@ struct DeviceLatch {
   }
 };
 
+// Resident CTAs per SM of a kernel that allocates tensor memory.  cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// answers 1 for such a kernel whatever it allocates, although CTAs whose columns fit the SM's 512 are resident
+// together (scripts/ubench/tmem_xchg.cu), so the budget is worked out from the kernel's own resources:
+// registers (allocated per warp in units of 8 per thread), shared memory (+ 1 KB the system reserves per CTA),
+// tensor-memory columns, 32 CTAs / 64 warps per SM.
+template <typename K>
+inline int tmem_ctas_per_sm(K kernel, int threads, int dyn_smem, int tm_cols) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 1;
+  int dev = 0, regs_sm = 65536, smem_sm = 233472;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  const int warps = (threads + 31) / 32;
+  const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * 32 * warps;
+  int n = regs_cta > 0 ? regs_sm / regs_cta : 32;
+  const int smem_cta = dyn_smem + (int)fa.sharedSizeBytes + 1024;
+  if (smem_sm / smem_cta < n) n = smem_sm / smem_cta;
+  if (tm_cols > 0 && 512 / tm_cols < n) n = 512 / tm_cols;
+  if (64 / warps < n) n = 64 / warps;
+  if (n > 32) n = 32;
+  return n < 1 ? 1 : n;
+}
+
 // ---- complex helpers -------------------------------------------------------
 template <typename T> struct cpx { T x, y; };
 template <typename T> struct vec2;

@@ -714,7 +714,7 @@ static int launch_engine(const EngineParams &P, cudaStream_t st) {
     return SDS_ENOTSUP;
   }
   // (the occupancy query answers 1 for a kernel that allocates tensor memory: sds_engine_f32.cu)
-  if (C::TM && per_sm < C::MINB) per_sm = C::MINB;
+  if (C::TM) per_sm = tmem_ctas_per_sm(engine_kernel<T, N, LEGS>, C::THREADS, C::SMEM, C::TM_COLS);
   engine_kernel<T, N, LEGS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
   SDS_LAUNCH_CHECK("engine_kernel");
   ++g_last_launches;

@@ -59,10 +59,12 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
   static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && (LEGS & ~LEG_THERMAL) == (LEG_DATA | LEG_NOISE) && !GAUSS &&
                                (N == 256 || (E3_F4 && N == 2048));
-  // TM1: the noise + fp64-thermal leg of the complex128 mode (one transform) makes its last exchange
-  // through tensor memory as well; its accumulators stay in registers (in tensor memory they measured
+  // TM1: the instantiations with ONE transform per row (data without noise; the noise + fp64-thermal leg
+  // of the complex128 mode) make their last exchange through tensor memory as well; their accumulators
+  // stay in registers (in tensor memory they measured
   // slower: 7.44 vs 5.96 ms, 80 words of read-modify-write per row and spills at 128 registers)
-  static constexpr bool TM1 = E3_TM && E3_TACC && LEGS == (LEG_NOISE | LEG_THERMAL64) && !GAUSS && TeamFftX<N>::TM_OK;
+  static constexpr bool TM1 = E3_TM && !((LEGS & LEG_DATA) && (LEGS & LEG_NOISE)) && (LEGS & (LEG_DATA | LEG_NOISE)) &&
+                              TeamFftX<N>::TM_OK;
   static constexpr int STAGES = TACC ? 2 : E3_STAGES;
   // tensor-memory columns of one warp (exchange 32 + accumulators 88), and of the CTA: warps w and w + 4
   // share TMEM lanes, so every set of four warps has its own column range
@@ -575,7 +577,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           Sn2[r] = fmaf(f2_lo(vn[r]), f2_lo(vn[r]), fmaf(f2_hi(vn[r]), f2_hi(vn[r]), Sn2[r]));
         }
       } else {
-        FFT::run(vd, fa, tw_s, tau, bar_id);
+        if (C::TM1) FFT::run_tm1(vd, fa, tw_s, tau, bar_id, tm_a);
+        else FFT::run(vd, fa, tw_s, tau, bar_id);
       }
       if (HAS_D) {
 #pragma unroll
@@ -895,11 +898,10 @@ static int launch_f32(const EngineParams &P, cudaStream_t st, int *launches) {
     set_error("sds_engine_run: kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
   }
-  // the occupancy query answers 1 for a kernel that allocates tensor memory, whatever it allocates;
-  // three CTAs with 32 of the 512 columns each are resident together (scripts/ubench/tmem_xchg.cu), and
-  // registers and shared memory are budgeted for MINB (the work queue is dynamic: a CTA that had to wait
-  // for an SM would still be correct)
-  if ((C::TM || C::TM1) && per_sm < C::MINB) per_sm = C::MINB;
+  // the occupancy query answers 1 for a kernel that allocates tensor memory, whatever it allocates: the
+  // grid is sized from the kernel's own register / shared-memory / column budget (the work queue is
+  // dynamic: a CTA that had to wait for an SM would still be correct)
+  if (C::TM || C::TM1) per_sm = tmem_ctas_per_sm(engine_f32_kernel<N, LEGS, GAUSS>, C::THREADS, C::SMEM, C::TM_COLS);
   engine_f32_kernel<N, LEGS, GAUSS><<<nsm * per_sm, C::THREADS, C::SMEM, st>>>(P);
   SDS_LAUNCH_CHECK("engine_f32_kernel");
   ++*launches;

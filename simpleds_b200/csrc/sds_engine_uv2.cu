@@ -451,7 +451,7 @@ static int launch_uv2(const EngineParams &P, cudaStream_t st, int *launches) {
   SDS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   SDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, engine_uv2_kernel<N, LEG>, C::THREADS, C::SMEM));
   // (the occupancy query answers 1 for a kernel that allocates tensor memory: sds_engine_f32.cu)
-  if (C::TM && per_sm < C::MINB) per_sm = C::MINB;
+  if (C::TM) per_sm = tmem_ctas_per_sm(engine_uv2_kernel<N, LEG>, C::THREADS, C::SMEM, 32);
   if (per_sm < 1) {
     set_error("sds_engine_run: two-set kernel does not fit an SM (smem %d B)", C::SMEM);
     return SDS_ENOTSUP;
