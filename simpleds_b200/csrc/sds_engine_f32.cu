@@ -63,8 +63,9 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // of the complex128 mode) make their last exchange through tensor memory as well; their accumulators
   // stay in registers (in tensor memory they measured
   // slower: 7.44 vs 5.96 ms, 80 words of read-modify-write per row and spills at 128 registers)
-  static constexpr bool TM1 = E3_TM && !((LEGS & LEG_DATA) && (LEGS & LEG_NOISE)) && (LEGS & (LEG_DATA | LEG_NOISE)) &&
-                              TeamFftX<N>::TM_OK;
+  static constexpr bool SINGLE = !((LEGS & LEG_DATA) && (LEGS & LEG_NOISE)) && (LEGS & (LEG_DATA | LEG_NOISE));
+  static constexpr bool F4S = E3_F4 && E3_TM && SINGLE && N == 2048;  // four-step, one transform per row
+  static constexpr bool TM1 = E3_TM && SINGLE && (TeamFftX<N>::TM_OK || F4S);
   static constexpr int STAGES = TACC ? 2 : E3_STAGES;
   // tensor-memory columns of one warp (exchange 32 + accumulators 88), and of the CTA: warps w and w + 4
   // share TMEM lanes, so every set of four warps has its own column range
@@ -85,7 +86,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   static constexpr int XROW = IL ? TeamFftX<N>::IL_BYTES : 2 * BUF;  // exchange bytes of one row
   static constexpr int XALIGN = IL ? 128 : BUF;
   static constexpr int XREGION = NWORKER * ROWS * XROW;  // all exchange buffers
-  static constexpr int TW_ENTRIES = (E3_F4 && E3_TM && E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE) && N == 2048)
+  static constexpr int TW_ENTRIES = (E3_F4 && E3_TM && N == 2048 && (SINGLE || (E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE))))
                                         ? TeamFft8x256::TW_TOTAL : fft_tw_total(N);
   static constexpr int TW_BYTES = ((TW_ENTRIES * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
@@ -126,11 +127,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   asm volatile("" : "+r"(sb_a));
 #endif
   f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
-  if constexpr (C::F4) {
+  if constexpr (C::F4 || C::F4S) {
     TeamFft8x256::fill_tables(tw_s, threadIdx.x, C::THREADS);
   } else {
     for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
-      tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[(C::TM || C::TM1) ? FFT::tm_tw_src(i) : i];
+      tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[(C::TM || C::TM1) ? FFT::tm_tw_src(i) : i];  // (not F4 / F4S: above)
   }
   // this row's exchange buffers: [xa, xa + BUF) and [xa + BUF, xa + 2 BUF)
   uint32_t xa = sb_a + (uint32_t)(wid * ROWS + sub) * C::XROW;
@@ -139,7 +140,9 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   asm volatile("" : "+r"(xa));
   asm volatile("" : "+r"(wb_a));
 #endif
-  const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : C::TM1 ? FFT::make_addr_p1(xa, tau) : FFT::make_addr(xa, tau);
+  const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : (C::TM1 && !C::F4S) ? FFT::make_addr_p1(xa, tau) : FFT::make_addr(xa, tau);
+  const typename TeamFftX<256>::Addr fa4s =
+      TeamFftX<256>::make_addr_p1(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION1, tau & 31);
   // four-step: the addresses of the warp-local 256-point transform in the warp's region of the row's buffer
   const typename TeamFftX<256>::Addr fa4 =
       TeamFftX<256>::make_addr_il(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION, tau & 31);
@@ -186,7 +189,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     tm_st_w16(tm_a + TC_PW, z16);
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
-  const int tau_out = C::F4 ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31) : (C::TM || C::TM1) ? FFT::tm_tau(tau) : tau;
+  const int tau_out = (C::F4 || C::F4S) ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31) : (C::TM || C::TM1) ? FFT::tm_tau(tau) : tau;
 
   // per-thread constants: taper * delta_f at this thread's 8 transform channels
   float tapdf[8];
@@ -555,6 +558,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
         } else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
+        else if constexpr (C::F4S) TeamFft8x256::run1(vn, xa, fa4s, tw_s, tau, bar_id, tm_a);
         else if (C::TM1) FFT::run_tm1(vn, fa, tw_s, tau, bar_id, tm_a);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
         if constexpr (C::TACC) {
@@ -577,7 +581,8 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           Sn2[r] = fmaf(f2_lo(vn[r]), f2_lo(vn[r]), fmaf(f2_hi(vn[r]), f2_hi(vn[r]), Sn2[r]));
         }
       } else {
-        if (C::TM1) FFT::run_tm1(vd, fa, tw_s, tau, bar_id, tm_a);
+        if constexpr (C::F4S) TeamFft8x256::run1(vd, xa, fa4s, tw_s, tau, bar_id, tm_a);
+        else if (C::TM1) FFT::run_tm1(vd, fa, tw_s, tau, bar_id, tm_a);
         else FFT::run(vd, fa, tw_s, tau, bar_id);
       }
       if (HAS_D) {

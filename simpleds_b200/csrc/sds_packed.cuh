@@ -694,6 +694,37 @@ struct TeamFft8x256 {
   static __device__ __forceinline__ void store(const f2 (&a)[8], const f2 (&b)[8], uint32_t xT, int tau) {
     store_t<0>(xT + 16u * (uint32_t)tau, a, b);
   }
+  // ---- one transform per row (data without noise; the noise leg of the complex128 mode) ----------------
+  // 8-byte slots: region k1 of REGION1 bytes, the warp-local transform on F256::run_tm1 in the same region
+  static constexpr int REGION1 = F256::P1_BYTES;
+  template <int k1> static __device__ __forceinline__ void store_t1(uint32_t st, const f2 (&a)[8]) {
+    if constexpr (k1 < 8) {
+      sts_f2_off<k1 * REGION1>(st, a[brev(k1, 3)]);
+      store_t1<k1 + 1>(st, a);
+    }
+  }
+  template <int r> static __device__ __forceinline__ void load_t1(uint32_t ld, f2 (&a)[8]) {
+    if constexpr (r < 8) {
+      a[r] = lds_f2_off<256 * r>(ld);
+      load_t1<r + 1>(ld, a);
+    }
+  }
+  // A: make_addr_p1(xT + (tau >> 5) REGION1, tau & 31).  The caller team-syncs between two calls (the step
+  // loop does, at the top of every step).
+  static __device__ __forceinline__ void run1(f2 (&a)[8], uint32_t xT, const typename F256::Addr &A,
+                                              const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
+    RadixP<8>::run(a);
+    store_t1<0>(xT + 8u * (uint32_t)tau, a);
+    f2 t[8];
+    twiddles(t, tw, tau);
+    team_sync<256>(bar);
+    const int w = tau >> 5, lane = tau & 31;
+    load_t1<0>(xT + (uint32_t)w * REGION1 + 8u * (uint32_t)lane, a);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = f2_cmul(a[r], t[r]);
+    __syncwarp();  // the warp has read its region; its own exchange may overwrite it
+    F256::run_tm1(a, A, tw + TW_A, lane, bar, tm);
+  }
   // the twiddles W_2048^(n2 k1) of the values this thread will own after the transposition (loaded in
   // the shadow of the team-wide exchange)
   static __device__ __forceinline__ void twiddles(f2 (&t)[8], const f2 *__restrict__ tw, int tau) {
