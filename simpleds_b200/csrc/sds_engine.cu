@@ -157,6 +157,66 @@ struct TeamFftD256 {
   }
 };
 
+// ---- complex128 transform of length 2048 = 8 x 256, four-step (as TeamFft8x256 of the fp32 engine) ----
+// One radix-8 pass across the 256-thread team, ONE team-wide exchange (16-byte slots: region k1 of 4608
+// bytes, position n2), then a 256-point transform per warp (TeamFftD256) in the warp's own region, with no
+// further team barrier.  On return lane l of warp w owns bins w + 8 (tm_tau(l) + 32 r).
+struct TeamFftD8x256 {
+  using D = TeamFftD256;
+  static constexpr int REGION = TeamFftX<256>::IL_BYTES;
+  static constexpr int XBYTES = 8 * REGION;
+  static constexpr int TW_A = 2048;                           // [k1][n2] W_2048^(n2 k1)
+  static constexpr int TW_TOTAL = TW_A + fft_tw_total(256);   // + the team table of length 256 (last pass permuted)
+  static __device__ __forceinline__ void fill_tables(cpx<double> *tab, int tid, int nthreads) {
+    for (int i = tid; i < TW_A; i += nthreads) {
+      const int k1 = i >> 8, n2 = i & 255;
+      double sn, cs;
+      sincospi(-2.0 * (double)((n2 * k1) & 2047) / 2048.0, &sn, &cs);
+      tab[i] = {cs, sn};
+    }
+    constexpr int NP = fft_npass(256);
+#pragma unroll
+    for (int p = 1; p < NP; ++p) {
+      const int R = fft_radix(256, p), NB = 8 / R, NS = fft_ns(256, p), off = fft_tw_offset(256, p);
+      for (int i = tid; i < NB * (R - 1) * 32; i += nthreads) {
+        const int tau = p == NP - 1 ? TeamFftX<256>::tm_tau(i & 31) : (i & 31);
+        const int mq = i >> 5, m = mq / (R - 1), q = mq % (R - 1) + 1;
+        const int k = (tau + 32 * m) % NS;
+        double sn, cs;
+        sincospi(-2.0 * (double)(q * k) / (double)(NS * R), &sn, &cs);
+        tab[TW_A + off + i] = {cs, sn};
+      }
+    }
+  }
+  template <int k1> static __device__ __forceinline__ void store_t(uint32_t st, const cpx<double> (&a)[8]) {
+    if constexpr (k1 < 8) {
+      sts_f2x2_off<k1 * REGION>(st, D::bits(a[brev(k1, 3)].x), D::bits(a[brev(k1, 3)].y));
+      store_t<k1 + 1>(st, a);
+    }
+  }
+  template <int r> static __device__ __forceinline__ void load_t(uint32_t ld, cpx<double> (&v)[8]) {
+    if constexpr (r < 8) {
+      unsigned long long re, im;
+      lds_f2x2_off<512 * r>(ld, re, im);
+      v[r] = {D::dbl(re), D::dbl(im)};
+      load_t<r + 1>(ld, v);
+    }
+  }
+  // (the caller team-syncs between two calls: the step loop does, at the top of every step)
+  static __device__ __forceinline__ void run(cpx<double> (&v)[8], uint32_t xT, const cpx<double> *__restrict__ tw,
+                                             int tau, int bar, uint32_t tm) {
+    Radix<double, 8>::run(v);
+    store_t<0>(xT + 16u * (uint32_t)tau, v);
+    team_sync<256>(bar);
+    const int w = tau >> 5, lane = tau & 31;
+    load_t<0>(xT + (uint32_t)w * REGION + 16u * (uint32_t)lane, v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], tw[w * 256 + lane + 32 * r]);
+    __syncwarp();  // the warp has read its region; its own exchange may overwrite it
+    D::run_tm(v, xT + (uint32_t)w * REGION, tw + TW_A, lane, tm);
+  }
+};
+
 // ---- the fused kernel ---------------------------------------------------------
 template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr int TPR = N / 8;
@@ -164,14 +224,18 @@ template <typename T, int N, int LEGS> struct EngCfg {
   static constexpr int ROWS = WORKER / TPR;            // rows per step
   static constexpr int THREADS = WORKER < 128 ? 128 : WORKER;
   static constexpr int NWORKER = THREADS / WORKER;
-  static constexpr int ROWB = 13 * N;                  // vis 8N | nsample 4N | flags N
+  // (the fp64 four-step data leg stages only what it reads: vis 8N | flags N -- two CTAs per SM)
+  static constexpr bool F4D = sizeof(T) == 8 && LEGS == LEG_DATA && N == 2048;
+  static constexpr int FL_OFF = F4D ? 8 * N : 12 * N;  // flags inside a staged row
+  static constexpr int ROWB = F4D ? 9 * N : 13 * N;    // vis 8N | nsample 4N | flags N
   static constexpr int SLOT = ROWS * ROWB;
   static constexpr int BUF = fft_buf_elems(N) * (int)sizeof(cpx<T>);
   // twiddle tables only for the legs of this instantiation (the data leg's in T, the noise
   // leg's in float): at N = 2048 in fp64 both tables, the ring and the exchange buffers
   // would not fit the 227 KB of an SM
   static constexpr bool SAME = sizeof(T) == sizeof(float);
-  static constexpr int TW_BYTES = (LEGS & LEG_DATA) ? fft_tw_total(N) * (int)sizeof(cpx<T>) : 0;
+  static constexpr int TW_BYTES = F4D ? TeamFftD8x256::TW_TOTAL * (int)sizeof(cpx<T>)
+                                  : (LEGS & LEG_DATA) ? fft_tw_total(N) * (int)sizeof(cpx<T>) : 0;
   static constexpr int TWF_BYTES =
       ((LEGS & LEG_NOISE) && !(SAME && (LEGS & LEG_DATA))) ? fft_tw_total(N) * (int)sizeof(cpx<float>) : 0;
   static constexpr int TAB_BYTES = ((TW_BYTES + TWF_BYTES + 127) / 128) * 128;
@@ -181,19 +245,21 @@ template <typename T, int N, int LEGS> struct EngCfg {
   // the fp64 data leg: a 2-slot ring leaves shared memory for three CTAs (12 warps) per SM at
   // N = 256, which beats the deeper prefetch at 8 warps (measured 7.23 -> 6.69 ms per HERA-350 batch)
   static constexpr bool D64 = sizeof(T) == 8 && LEGS == LEG_DATA;
-  static constexpr bool TM = D64 && N == 256;  // last exchange through tensor memory (TeamFftD256)
+  static constexpr bool TM = D64 && (N == 256 || F4D);  // last exchange through tensor memory (TeamFftD256)
 #ifndef ENG_D64_TACC
 #define ENG_D64_TACC 1
 #endif
   // the fp64 accumulators (S1: 32 words, S2: 16, the per-time sums: 16) in thread-private tensor-memory
   // columns [32, 96), as in the fp32 engine: 128 registers, four CTAs per SM
   static constexpr bool TACC = TM && ENG_D64_TACC;
-  static constexpr int TM_COLS = TACC ? 128 : 32;
+  static constexpr int TM_WCOLS = TACC ? 128 : 32;             // per set of four warps (they share TMEM lanes)
+  static constexpr int TM_COLS = TM_WCOLS * (THREADS / 128);
   // the thermal leg transforms nothing: no exchange buffers, and a register budget for 16 warps / SM
-  static constexpr int XB_BYTES = TM ? ROWS * TeamFftX<256>::IL_BYTES : (LEGS & (LEG_DATA | LEG_NOISE)) ? 2 * ROWS * BUF : 0;
+  static constexpr int XB_BYTES = F4D ? TeamFftD8x256::XBYTES : TM ? ROWS * TeamFftX<256>::IL_BYTES
+                                  : (LEGS & (LEG_DATA | LEG_NOISE)) ? 2 * ROWS * BUF : 0;
   static constexpr int STAGES = D64 ? 2 : ENG_STAGES;
   static constexpr int MINB = (LEGS == LEG_THERMAL) ? (512 / THREADS < 1 ? 1 : 512 / THREADS)
-                              : TACC ? 4 : D64 ? (384 / THREADS < 1 ? 1 : 384 / THREADS) : ENG_MINBLOCKS;
+                              : TACC ? 512 / THREADS : D64 ? (384 / THREADS < 1 ? 1 : 384 / THREADS) : ENG_MINBLOCKS;
   static constexpr int WORKER_BYTES = 64 + STAGES * SLOT + XB_BYTES + NB_BYTES;
   static constexpr int SMEM = TAB_BYTES + NWORKER * WORKER_BYTES;
 };
@@ -212,9 +278,13 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   cpx<T> *tw_s = reinterpret_cast<cpx<T> *>(smem);
   cpx<float> *twf_s = SAME ? reinterpret_cast<cpx<float> *>(smem)
                            : reinterpret_cast<cpx<float> *>(smem + C::TW_BYTES);
-  for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS) {
-    if (C::TW_BYTES) tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[C::TM ? TeamFftX<N>::tm_tw_src(i) : i];
-    if (C::TWF_BYTES) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
+  if constexpr (C::F4D) {
+    TeamFftD8x256::fill_tables(reinterpret_cast<cpx<double> *>(smem), threadIdx.x, C::THREADS);
+  } else {
+    for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS) {
+      if (C::TW_BYTES) tw_s[i] = reinterpret_cast<const cpx<T> *>(P.tw)[C::TM ? TeamFftX<N>::tm_tw_src(i) : i];
+      if (C::TWF_BYTES) twf_s[i] = {P.tw_f[i].x, P.tw_f[i].y};
+    }
   }
   const int wid = threadIdx.x / WORKER, wl = threadIdx.x % WORKER;
   const int sub = wl / TPR, tau = wl % TPR, bar_id = 1 + wid;
@@ -235,10 +305,12 @@ engine_kernel(const __grid_constant__ EngineParams P) {
   uint32_t tm_a = 0;
   if (C::TM) {
     tm_fence_after();
-    tm_a = tm_base_s + ((((uint32_t)threadIdx.x >> 5) & 3u) * 32u << 16);
+    const uint32_t warp = (uint32_t)threadIdx.x >> 5;
+    tm_a = tm_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)C::TM_WCOLS;
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
-  const int tau_out = C::TM ? TeamFftX<256>::tm_tau(tau & 31) : tau;
+  const int tau_out = C::F4D ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31)
+                      : C::TM ? TeamFftX<256>::tm_tau(tau & 31) : tau;
   uint32_t xa_tm = smem_u32(stages + C::STAGES * C::SLOT);  // TM: one exchange region per worker (ROWS = 1)
   asm volatile("" : "+r"(xa_tm));
   constexpr uint32_t TC_S1 = 32, TC_S2 = 64, TC_PW = 80;
@@ -308,7 +380,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
         for (int rr = 0; rr < nact; ++rr, e += row_stride, dst += C::ROWB) {
           if (HAS_D) tma_load_1d(dst, P.vis + e, 8 * N, &full[slot_p]);
           if (HAS_N || HAS_T) tma_load_1d(dst + 8 * N, P.nsample + e, 4 * N, &full[slot_p]);
-          if (HAS_D || HAS_N) tma_load_1d(dst + 12 * N, P.flags + e, N, &full[slot_p]);
+          if (HAS_D || HAS_N) tma_load_1d(dst + C::FL_OFF, P.flags + e, N, &full[slot_p]);
         }
       }
       slot_p = slot_p + 1 == C::STAGES ? 0 : slot_p + 1;
@@ -378,7 +450,7 @@ engine_kernel(const __grid_constant__ EngineParams P) {
       const unsigned char *row = stages + slot_c * C::SLOT + sub * C::ROWB;
       const float2 *vis_s = reinterpret_cast<const float2 *>(row);
       const float *ns_s = reinterpret_cast<const float *>(row + 8 * N);
-      const unsigned char *fl_s = row + 12 * N;
+      const unsigned char *fl_s = row + C::FL_OFF;
 
       uint32_t keep = 0;  // bit r set: channel tau + TPR r of an active row is unflagged
       if (HAS_D || HAS_N) {
@@ -395,7 +467,8 @@ engine_kernel(const __grid_constant__ EngineParams P) {
           const T m = (keep >> r) & 1u ? tapdf[r] : (T)0;  // (1 - flag) * taper * df
           v[r] = {(T)c.x * m, (T)c.y * m};
         }
-        if constexpr (C::TM) TeamFftD256::run_tm(v, xa_tm, tw_s, tau, tm_a);
+        if constexpr (C::F4D) TeamFftD8x256::run(v, xa_tm, reinterpret_cast<const cpx<double> *>(tw_s), tau, bar_id, tm_a);
+        else if constexpr (C::TM) TeamFftD256::run_tm(v, xa_tm, tw_s, tau, tm_a);
         else TeamFft<T, N>::run(v, bufA, bufB, tw_s, tau, bar_id);
         if constexpr (C::TACC) {  // (the exchange inside the transform fenced the stores of the previous row)
           uint32_t w32[32], w16[16];
