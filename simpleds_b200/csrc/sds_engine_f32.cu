@@ -57,7 +57,7 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // TACC: every per-item accumulator (pair sums, |x|^2 sums, thermal sums, the per-time |S1|^2 sums) lives
   // in thread-private tensor-memory columns and is read-modified-written once per row with one
   // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
-  static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && (LEGS & ~LEG_THERMAL) == (LEG_DATA | LEG_NOISE) && !GAUSS &&
+  static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && (LEGS & ~LEG_THERMAL) == (LEG_DATA | LEG_NOISE) &&
                                (N == 256 || (E3_F4 && N == 2048));
   // TM1: the instantiations with ONE transform per row (data without noise; the noise + fp64-thermal leg
   // of the complex128 mode) make their last exchange through tensor memory as well; their accumulators
