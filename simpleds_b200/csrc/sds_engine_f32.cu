@@ -30,7 +30,8 @@ namespace sds {
 #define E3_TACC 1  // accumulators in tensor memory: 128 registers, 16 warps per SM (N = 256, three legs)
 #endif
 #ifndef E3_F4
-#define E3_F4 1  // N = 2048: one team-wide exchange, then one 256-point transform per warp (TeamFft8x256)
+#define E3_F4 1  // N = 1024, 2048: one team-wide exchange, then one 256-point transform per warp (TeamFftRx256);
+                 // at N = 512 (two-warp teams) the generic schedule measured 3 % faster (0.486 vs 0.473)
 #endif
 #ifndef E3_KEEP
 #define E3_KEEP 1
@@ -44,6 +45,7 @@ namespace sds {
 // GAUSS: the in-kernel draw is Box-Muller per channel (noise_mode 3) instead of the moment-matched
 // discrete law (noise_mode 1); injected noise (mode 2) runs in the GAUSS = false instantiation
 template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
+  using F4T = TeamFftRx256<(N >= 512 ? N / 256 : 8)>;  // the four-step transform of this length (N >= 512)
   // the noise leg alone (complex128 mode) keeps neither visibilities nor the data accumulators:
   // 122 registers and 5 N staged bytes per row let 16 warps per SM run it
   static constexpr bool NOISE_ONLY = LEGS == LEG_NOISE;
@@ -58,13 +60,13 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // in thread-private tensor-memory columns and is read-modified-written once per row with one
   // instruction per 16 / 32 words: 72 registers fewer, 128 registers per thread, four CTAs per SM
   static constexpr bool TACC = E3_TACC && E3_TM && E3_IL && (LEGS & ~LEG_THERMAL) == (LEG_DATA | LEG_NOISE) &&
-                               (N == 256 || (E3_F4 && N == 2048));
+                               (N == 256 || (E3_F4 && N >= 1024));
   // TM1: the instantiations with ONE transform per row (data without noise; the noise + fp64-thermal leg
   // of the complex128 mode) make their last exchange through tensor memory as well; their accumulators
   // stay in registers (in tensor memory they measured
   // slower: 7.44 vs 5.96 ms, 80 words of read-modify-write per row and spills at 128 registers)
   static constexpr bool SINGLE = !((LEGS & LEG_DATA) && (LEGS & LEG_NOISE)) && (LEGS & (LEG_DATA | LEG_NOISE));
-  static constexpr bool F4S = E3_F4 && E3_TM && SINGLE && N == 2048;  // four-step, one transform per row
+  static constexpr bool F4S = E3_F4 && E3_TM && SINGLE && N >= 1024;  // four-step, one transform per row
   static constexpr bool TM1 = E3_TM && SINGLE && (TeamFftX<N>::TM_OK || F4S);
   static constexpr int STAGES = TACC ? 2 : E3_STAGES;
   // tensor-memory columns of one warp (exchange 32 + accumulators 88), and of the CTA: warps w and w + 4
@@ -81,13 +83,13 @@ template <int N, int LEGS, bool GAUSS = false> struct E3Cfg {
   // slots with 128-bit accesses (TeamFftX::run2_il): 18 N bytes per row, no alignment requirement;
   // otherwise a pair of XOR-addressed buffers of 8 N bytes, aligned to 8 N
   static constexpr bool IL = E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE);
-  static constexpr bool F4 = E3_F4 && E3_TM && IL && N == 2048;
+  static constexpr bool F4 = E3_F4 && E3_TM && IL && N >= 1024;
   static constexpr bool TM = E3_TM && IL && (TeamFftX<N>::TM_OK || F4);
   static constexpr int XROW = IL ? TeamFftX<N>::IL_BYTES : 2 * BUF;  // exchange bytes of one row
   static constexpr int XALIGN = IL ? 128 : BUF;
   static constexpr int XREGION = NWORKER * ROWS * XROW;  // all exchange buffers
-  static constexpr int TW_ENTRIES = (E3_F4 && E3_TM && N == 2048 && (SINGLE || (E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE))))
-                                        ? TeamFft8x256::TW_TOTAL : fft_tw_total(N);
+  static constexpr int TW_ENTRIES = (E3_F4 && E3_TM && N >= 1024 && (SINGLE || (E3_IL && (LEGS & LEG_DATA) && (LEGS & LEG_NOISE))))
+                                        ? F4T::TW_TOTAL : fft_tw_total(N);
   static constexpr int TW_BYTES = ((TW_ENTRIES * 8 + 127) / 128) * 128;
   // per worker: 64 B barriers | 128 B integration times of 32 steps | E3_STAGES slots | 2 N floats (P sums)
   static constexpr int HEAD = 448;  // 64 B barriers | 128 B t_int^-1/2 of 32 steps | 256 B 1 / t_int in fp64 (T64)
@@ -108,6 +110,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
   static_assert(!(HAS_T && T64), "thermal sums are fp32 or fp64, not both");
   using C = E3Cfg<N, LEGS, GAUSS>;
   using FFT = TeamFftX<N>;
+  using F4T = typename C::F4T;
   constexpr int TPR = C::TPR, TEAM = C::TEAM, ROWS = C::ROWS;
   constexpr bool TV = E3_TV && ROWS == 1 && (HAS_N || HAS_T || T64);  // integration times as a lane vector
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -128,7 +131,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #endif
   f2 *tw_s = reinterpret_cast<f2 *>(__cvta_shared_to_generic(sb_a + C::XREGION));
   if constexpr (C::F4 || C::F4S) {
-    TeamFft8x256::fill_tables(tw_s, threadIdx.x, C::THREADS);
+    F4T::fill_tables(tw_s, threadIdx.x, C::THREADS);
   } else {
     for (int i = threadIdx.x; i < fft_tw_total(N); i += C::THREADS)
       tw_s[i] = reinterpret_cast<const f2 *>(P.tw_f)[(C::TM || C::TM1) ? FFT::tm_tw_src(i) : i];  // (not F4 / F4S: above)
@@ -142,10 +145,10 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
 #endif
   const typename FFT::Addr fa = C::IL ? FFT::make_addr_il(xa, tau) : (C::TM1 && !C::F4S) ? FFT::make_addr_p1(xa, tau) : FFT::make_addr(xa, tau);
   const typename TeamFftX<256>::Addr fa4s =
-      TeamFftX<256>::make_addr_p1(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION1, tau & 31);
+      TeamFftX<256>::make_addr_p1(xa + (uint32_t)(tau >> 5) * F4T::REGION1, tau & 31);
   // four-step: the addresses of the warp-local 256-point transform in the warp's region of the row's buffer
   const typename TeamFftX<256>::Addr fa4 =
-      TeamFftX<256>::make_addr_il(xa + (uint32_t)(tau >> 5) * TeamFft8x256::REGION, tau & 31);
+      TeamFftX<256>::make_addr_il(xa + (uint32_t)(tau >> 5) * F4T::REGION, tau & 31);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(__cvta_shared_to_generic(wb_a));
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *stages = wbase + C::HEAD;
@@ -189,7 +192,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
     tm_st_w16(tm_a + TC_PW, z16);
   }
   // the spectrum bins a thread owns: tau_out + TPR r (the tensor-memory exchange renames the lanes)
-  const int tau_out = (C::F4 || C::F4S) ? (tau >> 5) + 8 * TeamFftX<256>::tm_tau(tau & 31) : (C::TM || C::TM1) ? FFT::tm_tau(tau) : tau;
+  const int tau_out = (C::F4 || C::F4S) ? (tau >> 5) + (N / 256) * TeamFftX<256>::tm_tau(tau & 31) : (C::TM || C::TM1) ? FFT::tm_tau(tau) : tau;
 
   // per-thread constants: taper * delta_f at this thread's 8 transform channels
   float tapdf[8];
@@ -525,10 +528,10 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
       if (HAS_N) {
         // both transforms in lockstep: two independent dependency chains per team sync
         if constexpr (C::F4) {
-          TeamFft8x256::front(vd, vn);
+          F4T::front(vd, vn);
           mbar_wait_a(free_a, par_f);  // every warp has made its last read of the previous row's buffer
           par_f ^= 1u;
-          TeamFft8x256::store(vd, vn, xa, tau);
+          F4T::store(vd, vn, xa, tau);
           // the row's ONE team-wide synchronisation as an arrive / wait pair on an mbarrier (one arrival
           // per warp), with the thermal sums in between; the "some sample of the row is invalid" vote
           // travels as the row's sequence number in one of two flag words (a word is rewritten two rows
@@ -544,7 +547,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
           if (HAS_T) thermal_sums();
           f2 tw4[8];
-          TeamFft8x256::twiddles(tw4, tw_s, tau);
+          F4T::twiddles(tw4, tw_s, tau);
           mbar_wait_a(stored_a, par_s);
           par_s ^= 1u;
           dirty_row = lds_u32(flag_a + 4u * (seq_f4 & 1u)) == seq_f4;
@@ -554,11 +557,11 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           }
           // all warps have consumed this row's slot: refill it (two rows ahead)
           if (pleft > 0) issue();
-          TeamFft8x256::back(vd, vn, tw4, xa, fa4, tw_s, tau, bar_id, tm_a, free_a);
+          F4T::back(vd, vn, tw4, xa, fa4, tw_s, tau, bar_id, tm_a, free_a);
         } else if (C::TM) FFT::run2_tm(vd, vn, fa, tw_s, tau, bar_id, tm_a);
         else if (C::IL) FFT::run2_il(vd, vn, fa, tw_s, tau, bar_id);
         else if (HAS_D) FFT::run2(vd, vn, fa, tw_s, tau, bar_id);
-        else if constexpr (C::F4S) TeamFft8x256::run1(vn, xa, fa4s, tw_s, tau, bar_id, tm_a);
+        else if constexpr (C::F4S) F4T::run1(vn, xa, fa4s, tw_s, tau, bar_id, tm_a);
         else if (C::TM1) FFT::run_tm1(vn, fa, tw_s, tau, bar_id, tm_a);
         else FFT::run(vn, fa, tw_s, tau, bar_id);
         if constexpr (C::TACC) {
@@ -581,7 +584,7 @@ engine_f32_kernel(const __grid_constant__ EngineParams P) {
           Sn2[r] = fmaf(f2_lo(vn[r]), f2_lo(vn[r]), fmaf(f2_hi(vn[r]), f2_hi(vn[r]), Sn2[r]));
         }
       } else {
-        if constexpr (C::F4S) TeamFft8x256::run1(vd, xa, fa4s, tw_s, tau, bar_id, tm_a);
+        if constexpr (C::F4S) F4T::run1(vd, xa, fa4s, tw_s, tau, bar_id, tm_a);
         else if (C::TM1) FFT::run_tm1(vd, fa, tw_s, tau, bar_id, tm_a);
         else FFT::run(vd, fa, tw_s, tau, bar_id);
       }

@@ -630,49 +630,65 @@ template <int N> struct TeamFftX {
   }
 };
 
-// ---- N = 2048 = 8 x 256, "four-step" -------------------------------------------------------------
-// The generic schedule runs a long row on a 256-thread team with a team-wide barrier per pass (three
-// of them at N = 2048).  Here the team makes ONE radix-8 pass (thread tau holds x[tau + 256 r]) and ONE
-// team-wide exchange -- a transposition after which warp w owns the 256 samples of residue k1 = w --
-// and then every warp runs its own 256-point transform on the warp-local machinery above (interleaved
-// exchange in the warp's region of the same buffer, tensor memory for the last exchange), with no
-// further team barrier:   X[k1 + 8 k2] = sum_n2 W_256^(n2 k2) [ W_2048^(n2 k1) sum_r x[n2 + 256 r] W_8^(r k1) ].
-// On return lane l of warp w holds bins  w + 8 (tm_tau(l) + 32 r).
-struct TeamFft8x256 {
+// ---- N = R x 256 (R = 2, 4, 8: N = 512, 1024, 2048), "four-step" -----------------------------------
+// The generic schedule runs a long row on a team of R warps with a team-wide barrier per pass (three of
+// them at N = 2048).  Here the team makes ONE radix-R pass (thread tau holds x[tau + 32 R r]: Q = 8 / R
+// butterflies over n1, for n2 = tau + 32 R j) and ONE team-wide exchange -- a transposition after which
+// warp w owns the 256 samples of residue k1 = w -- and then every warp runs its own 256-point transform
+// on the warp-local machinery above (interleaved exchange in the warp's region of the same buffer, tensor
+// memory for the last exchange), with no further team barrier:
+//   X[k1 + R k2] = sum_n2 W_256^(n2 k2) [ W_N^(n2 k1) sum_n1 x[n2 + 256 n1] W_R^(n1 k1) ].
+// On return lane l of warp w holds bins  w + R (tm_tau(l) + 32 r)  =  (w + R tm_tau(l)) + 32 R r.
+template <int R> struct TeamFftRx256 {
+  static_assert(R == 2 || R == 4 || R == 8, "N = 512, 1024 or 2048");
   using F256 = TeamFftX<256>;
-  static constexpr int N = 2048;
+  static constexpr int N = 256 * R, TEAM = 32 * R, Q = 8 / R, LGR = ilog2(R);
   static constexpr int REGION = F256::IL_BYTES;            // 4608 B: one warp's padded exchange region
-  static constexpr int XBYTES = 8 * REGION;                // the row's exchange bytes (= 18 N)
-  static constexpr int TW_A = 2048;                        // [k1][n2] W_2048^(n2 k1)
+  static constexpr int XBYTES = R * REGION;                // the row's exchange bytes (= 18 N)
+  static constexpr int TW_A = N;                           // [k1][n2] W_N^(n2 k1)
   static constexpr int TW_TOTAL = TW_A + fft_tw_total(256);  // + the team table of length 256
   // tables computed by the CTA itself (sincospi of exact arguments), no plan storage
   static __device__ __forceinline__ void fill_tables(f2 *tab, int tid, int nthreads) {
     for (int i = tid; i < TW_A; i += nthreads) {
       const int k1 = i >> 8, n2 = i & 255;
       float sn, cs;
-      sincospif(-2.0f * (float)((n2 * k1) & 2047) / 2048.0f, &sn, &cs);
+      sincospif(-2.0f * (float)((n2 * k1) & (N - 1)) / (float)N, &sn, &cs);
       tab[i] = f2_make(cs, sn);
     }
     constexpr int NP = fft_npass(256);
 #pragma unroll
     for (int p = 1; p < NP; ++p) {
-      const int R = fft_radix(256, p), NB = 8 / R, NS = fft_ns(256, p), off = fft_tw_offset(256, p);
-      for (int i = tid; i < NB * (R - 1) * 32; i += nthreads) {
+      const int RR = fft_radix(256, p), NB = 8 / RR, NS = fft_ns(256, p), off = fft_tw_offset(256, p);
+      for (int i = tid; i < NB * (RR - 1) * 32; i += nthreads) {
         // (last pass: the column of lane l holds the twiddle of team member tm_tau(l), see tm_tw_src)
         const int tau = p == NP - 1 ? F256::tm_tau(i & 31) : (i & 31);
-        const int mq = i >> 5, m = mq / (R - 1), q = mq % (R - 1) + 1;
+        const int mq = i >> 5, m = mq / (RR - 1), q = mq % (RR - 1) + 1;
         const int k = (tau + 32 * m) % NS;
         float sn, cs;
-        sincospif(-2.0f * (float)(q * k) / (float)(NS * R), &sn, &cs);
+        sincospif(-2.0f * (float)(q * k) / (float)(NS * RR), &sn, &cs);
         tab[TW_A + off + i] = f2_make(cs, sn);
       }
     }
   }
-  template <int k1>
+  // the radix-R pass: slot j + Q k1 holds output k1 of butterfly j afterwards
+  static __device__ __forceinline__ void radix_pass(f2 (&a)[8]) {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      f2 x[R];
+#pragma unroll
+      for (int n1 = 0; n1 < R; ++n1) x[n1] = a[j + Q * n1];
+      RadixP<R>::run(x);
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) a[j + Q * k1] = x[brev(k1, LGR)];
+    }
+  }
+  // value (k1, n2 = tau + TEAM j) -> region k1, slot n2; warp w then reads slots lane + 32 r of region w
+  template <int s>
   static __device__ __forceinline__ void store_t(uint32_t st, const f2 (&a)[8], const f2 (&b)[8]) {
-    if constexpr (k1 < 8) {
-      sts_f2x2_off<k1 * REGION>(st, a[brev(k1, 3)], b[brev(k1, 3)]);
-      store_t<k1 + 1>(st, a, b);
+    if constexpr (s < 8) {
+      constexpr int j = s % Q, k1 = s / Q;
+      sts_f2x2_off<k1 * REGION + 16 * TEAM * j>(st, a[s], b[s]);
+      store_t<s + 1>(st, a, b);
     }
   }
   template <int r>
@@ -683,13 +699,13 @@ struct TeamFft8x256 {
     }
   }
   // xT: the row's exchange buffer; A: make_addr_il(xT + (tau >> 5) REGION, tau & 31); tw: the tables above.
-  // front: the radix-8 pass; the caller then waits until the team has released the buffer (free_bar of
-  // the previous row), calls store, makes ONE team-wide barrier, and calls back -- which releases the
-  // buffer (free_bar) as soon as the warp has made its last read of its region.  Between back and the
+  // front: the radix-R pass; the caller then waits until the team has released the buffer (free_bar of
+  // the previous row), calls store, makes ONE team-wide synchronisation, and calls back -- which releases
+  // the buffer (free_bar) as soon as the warp has made its last read of its region.  Between back and the
   // next store a warp runs free of the team.
   static __device__ __forceinline__ void front(f2 (&a)[8], f2 (&b)[8]) {
-    RadixP<8>::run(a);
-    RadixP<8>::run(b);
+    radix_pass(a);
+    radix_pass(b);
   }
   static __device__ __forceinline__ void store(const f2 (&a)[8], const f2 (&b)[8], uint32_t xT, int tau) {
     store_t<0>(xT + 16u * (uint32_t)tau, a, b);
@@ -697,10 +713,11 @@ struct TeamFft8x256 {
   // ---- one transform per row (data without noise; the noise leg of the complex128 mode) ----------------
   // 8-byte slots: region k1 of REGION1 bytes, the warp-local transform on F256::run_tm1 in the same region
   static constexpr int REGION1 = F256::P1_BYTES;
-  template <int k1> static __device__ __forceinline__ void store_t1(uint32_t st, const f2 (&a)[8]) {
-    if constexpr (k1 < 8) {
-      sts_f2_off<k1 * REGION1>(st, a[brev(k1, 3)]);
-      store_t1<k1 + 1>(st, a);
+  template <int s> static __device__ __forceinline__ void store_t1(uint32_t st, const f2 (&a)[8]) {
+    if constexpr (s < 8) {
+      constexpr int j = s % Q, k1 = s / Q;
+      sts_f2_off<k1 * REGION1 + 8 * TEAM * j>(st, a[s]);
+      store_t1<s + 1>(st, a);
     }
   }
   template <int r> static __device__ __forceinline__ void load_t1(uint32_t ld, f2 (&a)[8]) {
@@ -709,28 +726,28 @@ struct TeamFft8x256 {
       load_t1<r + 1>(ld, a);
     }
   }
+  // the twiddles W_N^(n2 k1) of the values this thread will own after the transposition (loaded in
+  // the shadow of the team-wide exchange)
+  static __device__ __forceinline__ void twiddles(f2 (&t)[8], const f2 *__restrict__ tw, int tau) {
+    const int w = tau >> 5, lane = tau & 31;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t[r] = tw[w * 256 + lane + 32 * r];
+  }
   // A: make_addr_p1(xT + (tau >> 5) REGION1, tau & 31).  The caller team-syncs between two calls (the step
   // loop does, at the top of every step).
   static __device__ __forceinline__ void run1(f2 (&a)[8], uint32_t xT, const typename F256::Addr &A,
                                               const f2 *__restrict__ tw, int tau, int bar, uint32_t tm) {
-    RadixP<8>::run(a);
+    radix_pass(a);
     store_t1<0>(xT + 8u * (uint32_t)tau, a);
     f2 t[8];
     twiddles(t, tw, tau);
-    team_sync<256>(bar);
+    team_sync<TEAM>(bar);
     const int w = tau >> 5, lane = tau & 31;
     load_t1<0>(xT + (uint32_t)w * REGION1 + 8u * (uint32_t)lane, a);
 #pragma unroll
     for (int r = 0; r < 8; ++r) a[r] = f2_cmul(a[r], t[r]);
     __syncwarp();  // the warp has read its region; its own exchange may overwrite it
     F256::run_tm1(a, A, tw + TW_A, lane, bar, tm);
-  }
-  // the twiddles W_2048^(n2 k1) of the values this thread will own after the transposition (loaded in
-  // the shadow of the team-wide exchange)
-  static __device__ __forceinline__ void twiddles(f2 (&t)[8], const f2 *__restrict__ tw, int tau) {
-    const int w = tau >> 5, lane = tau & 31;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) t[r] = tw[w * 256 + lane + 32 * r];
   }
   static __device__ __forceinline__ void back(f2 (&a)[8], f2 (&b)[8], const f2 (&t)[8], uint32_t xT,
                                               const typename F256::Addr &A, const f2 *__restrict__ tw, int tau,
@@ -746,6 +763,7 @@ struct TeamFft8x256 {
     F256::run2_tm(a, b, A, tw + TW_A, lane, bar, tm, free_bar);
   }
 };
+using TeamFft8x256 = TeamFftRx256<8>;
 
 // ---- small helpers shared by the fused engines ------------------------------------------------
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
